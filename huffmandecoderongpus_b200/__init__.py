@@ -1,0 +1,374 @@
+"""huffmandecoderongpus_b200 -- ctypes binding of libhuffb200.so (include/huffb200.h).
+
+The product is the C-ABI shared library (hand-written sm_100a CUDA + C host
+code); this module only exposes it to Python tests and bench.py.  There is no
+Python or CPU decode path: if the library is missing, or no CUDA device is
+present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
+
+HB_OK = 0
+ERRORS = {
+    -1: "HB_ERR_CUDA", -2: "HB_ERR_TREE", -3: "HB_ERR_CODELEN", -4: "HB_ERR_ARG",
+    -5: "HB_ERR_NOMEM", -6: "HB_ERR_OUTPUT_FULL", -7: "HB_ERR_IO", -8: "HB_ERR_FORMAT",
+    -9: "HB_ERR_STATE",
+}
+
+MODEL_ENGLISH, MODEL_FIBONACCI, MODEL_DNA, MODEL_UNIFORM8 = 0, 1, 2, 3
+
+NODE_DTYPE = np.dtype([("sym", np.uint8), ("izero", np.int32), ("ione", np.int32)], align=True)
+
+
+class HuffError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: {ERRORS.get(code, code)} {detail}".strip())
+
+
+class Node(C.Structure):
+    _fields_ = [("sym", C.c_uint8), ("izero", C.c_int32), ("ione", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_symbols", C.c_uint64), ("out_base", C.c_uint64),
+                ("exit_offset", C.c_uint32), ("entry_offset", C.c_uint32),
+                ("launches", C.c_uint32), ("tiles", C.c_uint32),
+                ("ms_total", C.c_float), ("ms_sync", C.c_float),
+                ("ms_scan", C.c_float), ("ms_emit", C.c_float)]
+
+
+class HuffFileC(C.Structure):
+    _fields_ = [("nodes", C.c_int32), ("wide", C.c_int32), ("bits", C.c_uint64),
+                ("usize", C.c_uint64), ("tree", C.POINTER(Node)),
+                ("data", C.POINTER(C.c_uint8))]
+
+
+class ModelC(C.Structure):
+    _fields_ = [("nodes", C.c_int32), ("tree", Node * 511), ("cum", C.c_uint32 * 256),
+                ("symtab", C.c_uint8 * 256), ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256),
+                ("maxlen", C.c_uint32), ("minlen", C.c_uint32), ("nsyms", C.c_uint32)]
+
+
+class LutC(C.Structure):
+    _fields_ = [("entries", C.POINTER(C.c_uint32)), ("n_entries", C.c_uint32),
+                ("w1", C.c_uint32), ("maxlen", C.c_uint32), ("minlen", C.c_uint32),
+                ("n_leaves", C.c_uint32), ("code", C.c_uint32 * 256),
+                ("codelen", C.c_uint8 * 256)]
+
+
+class RefCompressedData(C.Structure):
+    """struct CompressedData, reference framework/huffdata.h:26-32"""
+    _fields_ = [("bits", C.c_int), ("nodes", C.c_int), ("uncompressedsize", C.c_int),
+                ("tree", C.c_void_p), ("data", C.c_void_p)]
+
+
+class RefUnCompressedData(C.Structure):
+    """struct UnCompressedData, reference framework/huffdata.h:34-37"""
+    _fields_ = [("uncompressedsize", C.c_int), ("data", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libhuffb200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C huffmandecoderongpus_b200` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "There is no Python/CPU fallback for the decode path.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.hb_strerror.restype = C.c_char_p
+    L.hb_strerror.argtypes = [i32]
+    L.hb_version.restype = C.c_char_p
+    L.hb_last_error.restype = C.c_char_p
+    L.hb_last_error.argtypes = [vp]
+    L.hb_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.hb_ctx_destroy.argtypes = [vp]
+    L.hb_ctx_destroy.restype = None
+    L.hb_ctx_configure.argtypes = [vp, i32, i32]
+    L.hb_ctx_sync.argtypes = [vp]
+    L.hb_ctx_timing_begin.argtypes = [vp, i32]
+    L.hb_ctx_timing_collect.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(i32)]
+    L.hb_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(u64)]
+    L.hb_codebook_create.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.hb_codebook_destroy.argtypes = [vp]
+    L.hb_codebook_destroy.restype = None
+    L.hb_codebook_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    L.hb_decode_device.argtypes = [vp, vp, vp, u64, u64, vp, u64, C.POINTER(Result)]
+    L.hb_shard_map.argtypes = [vp, vp, vp, u64, u64, u64, vp]
+    L.hb_shard_compose.argtypes = [vp, vp, i32, i32, vp]
+    L.hb_shard_emit.argtypes = [vp, vp, vp, u64, u64, u64, vp, vp, u64, C.POINTER(Result)]
+    L.hb_decode_host.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
+    L.hb_huff_load.argtypes = [C.c_char_p, C.POINTER(HuffFileC)]
+    L.hb_huff_save.argtypes = [C.c_char_p, C.POINTER(HuffFileC), i32]
+    L.hb_huff_free.argtypes = [C.POINTER(HuffFileC)]
+    L.hb_huff_free.restype = None
+    L.hb_model_build.argtypes = [i32, C.POINTER(ModelC)]
+    L.hb_gen_symbols_cpu.argtypes = [C.POINTER(ModelC), u64, u64, u64, vp]
+    L.hb_gen_symbols_cpu.restype = None
+    L.hb_encode_bits_cpu.argtypes = [C.POINTER(ModelC), vp, u64]
+    L.hb_encode_bits_cpu.restype = u64
+    L.hb_encode_cpu.argtypes = [C.POINTER(ModelC), vp, u64, vp]
+    L.hb_encode_cpu.restype = None
+    L.hb_gen_encode_device.argtypes = [vp, C.POINTER(ModelC), u64, u64, u64, vp, u64, C.POINTER(u64)]
+    L.hb_gen_verify_device.argtypes = [vp, C.POINTER(ModelC), u64, u64, u64, vp, C.POINTER(u64)]
+    L.hb_gen_count_bits_device.argtypes = [vp, C.POINTER(ModelC), u64, u64, u64, C.POINTER(u64)]
+    L.hb_lut_build.argtypes = [vp, i32, i32, i32, C.POINTER(LutC)]
+    L.hb_lut_free.argtypes = [C.POINTER(LutC)]
+    L.hb_lut_free.restype = None
+    for name in ("b200Approach",):
+        f = getattr(L, name)
+        f.restype = None
+        f.argtypes = [C.POINTER(RefCompressedData), C.POINTER(RefUnCompressedData), vp]
+    L.b200ApproachLastDeviceMs.restype = C.c_double
+    L.b200ApproachLastSymbols.restype = C.c_ulonglong
+    L.b200ApproachShutdown.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc, where, ctx=None):
+    if rc != HB_OK:
+        detail = ""
+        if ctx is not None and rc == -1:
+            detail = lib().hb_last_error(ctx).decode(errors="replace")
+        raise HuffError(rc, where, detail)
+
+
+# ---- host-side pieces (no GPU needed) ----------------------------------------
+
+class HuffFile:
+    """A .huff stream loaded by the C host loader (hb_huff_load)."""
+
+    def __init__(self, tree, data, bits, usize, wide=False):
+        self.tree = np.ascontiguousarray(tree, dtype=NODE_DTYPE)
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.bits = int(bits)
+        self.usize = int(usize)
+        self.wide = bool(wide)
+        self.nodes = int(self.tree.shape[0])
+
+    @property
+    def nbytes(self):
+        return (self.bits + 7) // 8
+
+    @classmethod
+    def load(cls, path):
+        f = HuffFileC()
+        _check(lib().hb_huff_load(os.fsencode(path), C.byref(f)), f"hb_huff_load({path})")
+        try:
+            tree = np.ctypeslib.as_array(C.cast(f.tree, C.POINTER(C.c_uint8)),
+                                         shape=(f.nodes * 12,)).copy().view(NODE_DTYPE)
+            nbytes = (f.bits + 7) // 8
+            data = np.ctypeslib.as_array(f.data, shape=(nbytes + 16,)).copy()
+            return cls(tree, data, f.bits, f.usize, f.wide)
+        finally:
+            lib().hb_huff_free(C.byref(f))
+
+    def save(self, path, wide=None):
+        wide = self.wide if wide is None else wide
+        f = HuffFileC(self.nodes, int(wide), self.bits, self.usize,
+                      C.cast(self.tree.ctypes.data, C.POINTER(Node)),
+                      C.cast(self.data.ctypes.data, C.POINTER(C.c_uint8)))
+        _check(lib().hb_huff_save(os.fsencode(path), C.byref(f), int(wide)), "hb_huff_save")
+
+
+def build_lut(tree, w1_max=0, w2_max=0):
+    """Host table construction (hb_lut_build); returns a dict of numpy data."""
+    tree = np.ascontiguousarray(tree, dtype=NODE_DTYPE)
+    lut = LutC()
+    _check(lib().hb_lut_build(tree.ctypes.data, int(tree.shape[0]), w1_max, w2_max, C.byref(lut)),
+           "hb_lut_build")
+    try:
+        return {
+            "entries": np.ctypeslib.as_array(lut.entries, shape=(lut.n_entries,)).copy(),
+            "w1": lut.w1, "maxlen": lut.maxlen, "minlen": lut.minlen, "n_leaves": lut.n_leaves,
+            "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
+        }
+    finally:
+        lib().hb_lut_free(C.byref(lut))
+
+
+class Model:
+    """Synthetic-stream model (hb_model_build): tree + sampler + code table."""
+
+    def __init__(self, kind):
+        self.kind = kind
+        self.c = ModelC()
+        _check(lib().hb_model_build(kind, C.byref(self.c)), "hb_model_build")
+        self.nodes = self.c.nodes
+        self.maxlen, self.minlen, self.nsyms = self.c.maxlen, self.c.minlen, self.c.nsyms
+        raw = np.frombuffer(bytes(self.c.tree), dtype=np.uint8)[: self.nodes * 12]
+        self.tree = raw.view(NODE_DTYPE).copy()
+
+    def symbols_cpu(self, seed, first, n):
+        out = np.empty(n, dtype=np.uint8)
+        lib().hb_gen_symbols_cpu(C.byref(self.c), seed, first, n, out.ctypes.data)
+        return out
+
+    def encode_cpu(self, syms):
+        syms = np.ascontiguousarray(syms, dtype=np.uint8)
+        bits = lib().hb_encode_bits_cpu(C.byref(self.c), syms.ctypes.data, syms.size)
+        out = np.zeros((bits + 7) // 8 + 32, dtype=np.uint8)
+        lib().hb_encode_cpu(C.byref(self.c), syms.ctypes.data, syms.size, out.ctypes.data)
+        return out, int(bits)
+
+    def huff_file_cpu(self, seed, n):
+        syms = self.symbols_cpu(seed, 0, n)
+        data, bits = self.encode_cpu(syms)
+        return HuffFile(self.tree, data, bits, n, wide=bits >= 2 ** 31), syms
+
+
+# ---- device objects -------------------------------------------------------------
+
+class Context:
+    def __init__(self, device=0, stream=None, words_per_thread=0, ctas_per_sm=0):
+        self.h = C.c_void_p()
+        _check(lib().hb_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)),
+               "hb_ctx_create (a CUDA device is required; there is no CPU fallback)")
+        self.device = device
+        if words_per_thread or ctas_per_sm:
+            self.configure(words_per_thread, ctas_per_sm)
+
+    def configure(self, words_per_thread=0, ctas_per_sm=0):
+        _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
+
+    def sync(self):
+        _check(lib().hb_ctx_sync(self.h), "hb_ctx_sync", self.h)
+
+    def timing_begin(self, max_steps):
+        _check(lib().hb_ctx_timing_begin(self.h, max_steps), "hb_ctx_timing_begin", self.h)
+
+    def timing_collect(self):
+        ms = (C.c_double * 4)()
+        n = C.c_int()
+        _check(lib().hb_ctx_timing_collect(self.h, C.byref(ms), C.byref(n)), "hb_ctx_timing_collect", self.h)
+        return {"sync": ms[0], "scan": ms[1], "emit": ms[2], "total": ms[3], "steps": n.value}
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        _check(lib().hb_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)),
+               "hb_device_info")
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def close(self):
+        if self.h:
+            lib().hb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Codebook:
+    def __init__(self, ctx: Context, tree):
+        self.ctx = ctx
+        tree = np.ascontiguousarray(tree, dtype=NODE_DTYPE)
+        self.h = C.c_void_p()
+        _check(lib().hb_codebook_create(ctx.h, tree.ctypes.data, int(tree.shape[0]), C.byref(self.h)),
+               "hb_codebook_create", ctx.h)
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().hb_codebook_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        self.maxlen, self.minlen, self.w1, self.n_entries = a.value, b.value, c.value, d.value
+
+    def close(self):
+        if self.h:
+            lib().hb_codebook_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _res_dict(r: Result):
+    return {k: getattr(r, k) for k, _ in Result._fields_}
+
+
+def decode_device(ctx: Context, cb: Codebook, d_comp: int, comp_bytes: int, bits: int,
+                  d_out: int, out_capacity: int):
+    """hb_decode_device on raw device pointers (e.g. torch tensor .data_ptr())."""
+    r = Result()
+    _check(lib().hb_decode_device(ctx.h, cb.h, d_comp, comp_bytes, bits, d_out, out_capacity,
+                                  C.byref(r)), "hb_decode_device", ctx.h)
+    return _res_dict(r)
+
+
+def shard_map(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_map):
+    _check(lib().hb_shard_map(ctx.h, cb.h, d_comp, comp_bytes, bits_own, bits_avail, d_map),
+           "hb_shard_map", ctx.h)
+
+
+def shard_compose(ctx, d_all_maps, n_ranks, rank, d_entry_base):
+    _check(lib().hb_shard_compose(ctx.h, d_all_maps, n_ranks, rank, d_entry_base),
+           "hb_shard_compose", ctx.h)
+
+
+def shard_emit(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_entry_base, d_out,
+               out_capacity, want_result=True):
+    r = Result()
+    _check(lib().hb_shard_emit(ctx.h, cb.h, d_comp, comp_bytes, bits_own, bits_avail,
+                               d_entry_base, d_out, out_capacity,
+                               C.byref(r) if want_result else None), "hb_shard_emit", ctx.h)
+    return _res_dict(r) if want_result else None
+
+
+def decode_host(ctx: Context, tree, data, bits: int, out: np.ndarray):
+    """hb_decode_host: host buffers in, host buffer out (upload, decode, download)."""
+    tree = np.ascontiguousarray(tree, dtype=NODE_DTYPE)
+    r = Result()
+    _check(lib().hb_decode_host(ctx.h, tree.ctypes.data, int(tree.shape[0]), data.ctypes.data, bits,
+                                out.ctypes.data, out.size, C.byref(r)), "hb_decode_host", ctx.h)
+    return _res_dict(r)
+
+
+def b200_approach(tree, data, bits: int, usize: int):
+    """Call the drop-in approach exactly as the reference's evaluate() would:
+    reference-layout structs, caller-allocated zeroed output of usize+3 bytes
+    (framework/decodeUtil.c:37-43).  Returns the output buffer [0:usize]."""
+    tree = np.ascontiguousarray(tree, dtype=NODE_DTYPE)
+    out = np.zeros(usize + 3, dtype=np.uint8)
+    cd = RefCompressedData(bits, int(tree.shape[0]), usize, tree.ctypes.data, data.ctypes.data)
+    ucd = RefUnCompressedData(usize, out.ctypes.data)
+    lib().b200Approach(C.byref(cd), C.byref(ucd), None)
+    return out[:usize]
+
+
+def gen_encode_device(ctx: Context, model: Model, seed: int, first: int, n: int, d_comp: int,
+                      capacity: int) -> int:
+    bits = C.c_uint64()
+    _check(lib().hb_gen_encode_device(ctx.h, C.byref(model.c), seed, first, n, d_comp, capacity,
+                                      C.byref(bits)), "hb_gen_encode_device", ctx.h)
+    return bits.value
+
+
+def gen_count_bits_device(ctx: Context, model: Model, seed: int, first: int, n: int) -> int:
+    bits = C.c_uint64()
+    _check(lib().hb_gen_count_bits_device(ctx.h, C.byref(model.c), seed, first, n, C.byref(bits)),
+           "hb_gen_count_bits_device", ctx.h)
+    return bits.value
+
+
+def gen_verify_device(ctx: Context, model: Model, seed: int, first: int, n: int, d_out: int) -> int:
+    bad = C.c_uint64()
+    _check(lib().hb_gen_verify_device(ctx.h, C.byref(model.c), seed, first, n, d_out, C.byref(bad)),
+           "hb_gen_verify_device", ctx.h)
+    return bad.value

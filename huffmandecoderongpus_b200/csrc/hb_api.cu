@@ -1,0 +1,551 @@
+/*
+ * hb_api.cu -- implementation of the C ABI declared in include/huffb200.h:
+ * context, codebook upload, kernel orchestration, timing.  No CPU decode path
+ * exists here: every decode entry point launches the sm_100a kernels or fails.
+ */
+#include "huffb200.h"
+#include "hb_lut.h"
+#include "hb_kernels.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#define HB_NEV 5
+
+struct hb_codebook {
+    hb_ctx *ctx;
+    hb_lut lut;        /* host copy (entries kept for the encoder / tests) */
+    uint32_t *d_lut;
+};
+
+struct hb_buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct hb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaDeviceProp prop;
+    int wpt = 4;
+    int ctas_per_sm = 0;
+    cudaEvent_t ev0[HB_NEV];   /* default event set */
+    cudaEvent_t *ev = nullptr; /* set used by the current step */
+    cudaEvent_t *tim_ev = nullptr; /* optional ring: tim_cap steps x HB_NEV events */
+    int tim_cap = 0, tim_n = 0;
+    char err[256];
+    /* scratch (grow-only) */
+    hb_buf subs, tmaps, wmaps, cmaps, cprefix, tile_entry, tile_base, misc;
+    /* misc layout (u64 words): [0..31] shard map, [32..35] result, [36] status, [40..42] zero entry_base */
+    /* state of the last hb_shard_map */
+    bool have_map = false;
+    uint32_t map_ntiles = 0, map_ncta = 0;
+    int map_wpt = 0;
+    /* host-buffer path */
+    hb_buf d_comp, d_out;
+    uint64_t *h_res = nullptr; /* pinned, 8 words */
+};
+
+static const char *const k_errs[] = {
+    "ok", "CUDA runtime error", "malformed Huffman tree", "codeword longer than 32 bits",
+    "bad argument", "out of memory", "output buffer too small", "I/O error",
+    "not a HUFF/HUF8 file", "call order",
+};
+
+extern "C" const char *hb_strerror(int code) {
+    int i = -code;
+    if (i < 0 || i >= (int)(sizeof(k_errs) / sizeof(k_errs[0]))) return "unknown error";
+    return k_errs[i];
+}
+
+extern "C" const char *hb_version(void) { return "huffb200 0.1 (sm_100a)"; }
+
+extern "C" const char *hb_last_error(const hb_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+static int cuda_fail(hb_ctx *ctx, cudaError_t e, const char *what) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    return HB_ERR_CUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);     \
+    } while (0)
+
+static int ensure(hb_ctx *ctx, hb_buf &b, size_t bytes) {
+    if (bytes <= b.cap) return HB_OK;
+    if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return HB_ERR_NOMEM;
+    }
+    b.cap = want;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_create(int device, void *cuda_stream, hb_ctx **out) {
+    if (!out) return HB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return HB_ERR_CUDA;   /* no CPU fallback */
+    }
+    hb_ctx *ctx = new (std::nothrow) hb_ctx();
+    if (!ctx) return HB_ERR_NOMEM;
+    ctx->err[0] = 0;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        delete ctx;
+        return HB_ERR_CUDA;
+    }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return HB_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    for (int i = 0; i < HB_NEV; i++) cudaEventCreate(&ctx->ev0[i]);
+    ctx->ev = ctx->ev0;
+    if (cudaMallocHost((void **)&ctx->h_res, 8 * sizeof(uint64_t)) != cudaSuccess) {
+        delete ctx;
+        return HB_ERR_CUDA;
+    }
+    *out = ctx;
+    return HB_OK;
+}
+
+extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    hb_buf *bufs[] = { &ctx->subs, &ctx->tmaps, &ctx->wmaps, &ctx->cmaps, &ctx->cprefix,
+                       &ctx->tile_entry, &ctx->tile_base, &ctx->misc, &ctx->d_comp, &ctx->d_out };
+    for (hb_buf *b : bufs) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < HB_NEV; i++) cudaEventDestroy(ctx->ev0[i]);
+    for (int i = 0; i < ctx->tim_cap * HB_NEV; i++) cudaEventDestroy(ctx->tim_ev[i]);
+    free(ctx->tim_ev);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm) {
+    if (!ctx) return HB_ERR_ARG;
+    if (words_per_thread != 0 && words_per_thread != 4 && words_per_thread != 8 &&
+        words_per_thread != 16)
+        return HB_ERR_ARG;
+    if (ctas_per_sm < 0 || ctas_per_sm > 32) return HB_ERR_ARG;
+    ctx->wpt = words_per_thread ? words_per_thread : 4;
+    ctx->ctas_per_sm = ctas_per_sm;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_sync(hb_ctx *ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+extern "C" int hb_device_info(hb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                              uint64_t *total_mem) {
+    if (!ctx) return HB_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (total_mem) *total_mem = (uint64_t)ctx->prop.totalGlobalMem;
+    return HB_OK;
+}
+
+/* ---- codebook ------------------------------------------------------------ */
+
+extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
+                                  hb_codebook **out) {
+    if (!ctx || !tree || !out) return HB_ERR_ARG;
+    *out = nullptr;
+    hb_codebook *cb = new (std::nothrow) hb_codebook();
+    if (!cb) return HB_ERR_NOMEM;
+    cb->ctx = ctx;
+    cb->d_lut = nullptr;
+    int rc = hb_lut_build(tree, nodes, 0, 0, &cb->lut);
+    if (rc != HB_OK) { delete cb; return rc; }
+    cudaSetDevice(ctx->device);
+    size_t bytes = sizeof(uint32_t) * (size_t)cb->lut.n_entries;
+    cudaError_t e = cudaMalloc((void **)&cb->d_lut, bytes);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cb->d_lut, cb->lut.entries, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (cb->d_lut) cudaFree(cb->d_lut);
+        hb_lut_free(&cb->lut);
+        delete cb;
+        return cuda_fail(ctx, e, "codebook upload");
+    }
+    *out = cb;
+    return HB_OK;
+}
+
+extern "C" void hb_codebook_destroy(hb_codebook *cb) {
+    if (!cb) return;
+    cudaSetDevice(cb->ctx->device);
+    if (cb->d_lut) cudaFree(cb->d_lut);
+    hb_lut_free(&cb->lut);
+    delete cb;
+}
+
+extern "C" int hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,
+                                uint32_t *w1, uint32_t *n_entries) {
+    if (!cb) return HB_ERR_ARG;
+    if (maxlen) *maxlen = cb->lut.maxlen;
+    if (minlen) *minlen = cb->lut.minlen;
+    if (w1) *w1 = cb->lut.w1;
+    if (n_entries) *n_entries = cb->lut.n_entries;
+    return HB_OK;
+}
+
+/* ---- launch helpers ------------------------------------------------------ */
+
+template <int WPT>
+static size_t sync_smem_bytes(uint32_t w1) {
+    return sizeof(uint32_t) * ((size_t)hb_lut_smem_words(w1) + HB_T * WPT + 4 +
+                               (size_t)WPT * HB_T + HB_T + HB_T + 16);
+}
+
+template <int WPT>
+static size_t emit_smem_bytes(uint32_t w1, uint32_t stage_bytes) {
+    return sizeof(uint32_t) * ((size_t)hb_lut_smem_words(w1) + HB_T * WPT + 4 + 16 + HB_T / 2) +
+           stage_bytes;
+}
+
+static uint32_t stage_bytes_for(int wpt, uint32_t minlen) {
+    /* at most ceil(S / minlen) codewords start in a subsequence; + alignment
+     * shift (<16) + one slack symbol per tile, rounded to 16 */
+    uint32_t S = 32u * (uint32_t)wpt;
+    uint32_t per = (S + minlen - 1) / minlen;
+    uint32_t b = HB_T * per + 16 + 16;
+    return (b + 15u) & ~15u;
+}
+
+template <typename K>
+static int grid_for(hb_ctx *ctx, K kernel, size_t smem, uint32_t ntiles, int *grid) {
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, HB_T, smem));
+    if (occ < 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "kernel does not fit an SM (smem %zu)", smem);
+        return HB_ERR_CUDA;
+    }
+    if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < occ) occ = ctx->ctas_per_sm;
+    uint64_t g = (uint64_t)occ * (uint64_t)ctx->prop.multiProcessorCount;
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return HB_OK;
+}
+
+static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uint64_t comp_bytes,
+                     uint64_t bits_own, uint64_t bits_avail, hb_stream_args *a) {
+    if (!ctx || !cb || cb->ctx != ctx) return HB_ERR_ARG;
+    if (bits_avail < bits_own) return HB_ERR_ARG;
+    if (bits_avail && !d_comp) return HB_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_comp) & 15u) != 0) return HB_ERR_ARG;
+    if (comp_bytes < (bits_avail + 7) / 8) return HB_ERR_ARG;
+    const uint64_t tile_bits = (uint64_t)HB_T * 32u * (uint64_t)ctx->wpt;
+    uint64_t ntiles = (bits_own + tile_bits - 1) / tile_bits;
+    if (ntiles > 0x7fffffffull) return HB_ERR_ARG;
+    a->words = (const uint32_t *)d_comp;
+    a->nwords = (comp_bytes + 3) / 4;   /* the word holding the last byte must be readable */
+    a->bits_own = bits_own;
+    a->bits_avail = bits_avail;
+    a->ntiles = (uint32_t)ntiles;
+    a->lut = cb->d_lut;
+    a->w1 = cb->lut.w1;
+    a->maxlen = cb->lut.maxlen;
+    return HB_OK;
+}
+
+static uint64_t *misc_words(hb_ctx *ctx) { return (uint64_t *)ctx->misc.p; }
+
+template <int WPT>
+static int launch_map(hb_ctx *ctx, const hb_stream_args &a, uint64_t *d_map) {
+    const uint32_t ncta = (a.ntiles + 1023u) / 1024u;
+    int rc;
+    if ((rc = ensure(ctx, ctx->subs, sizeof(uint16_t) * (size_t)a.ntiles * HB_T))) return rc;
+    if ((rc = ensure(ctx, ctx->tmaps, sizeof(uint32_t) * (size_t)a.ntiles * 32))) return rc;
+    if ((rc = ensure(ctx, ctx->wmaps, sizeof(uint64_t) * (size_t)ncta * 32 * 32))) return rc;
+    if ((rc = ensure(ctx, ctx->cmaps, sizeof(uint64_t) * (size_t)ncta * 32))) return rc;
+    if ((rc = ensure(ctx, ctx->cprefix, sizeof(uint64_t) * (size_t)ncta * 32))) return rc;
+    if ((rc = ensure(ctx, ctx->tile_entry, (size_t)a.ntiles))) return rc;
+    if ((rc = ensure(ctx, ctx->tile_base, sizeof(uint64_t) * (size_t)a.ntiles))) return rc;
+
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    size_t smem = sync_smem_bytes<WPT>(a.w1);
+    int grid = 1;
+    if ((rc = grid_for(ctx, hb_sync_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
+    hb_sync_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(a, (uint16_t *)ctx->subs.p,
+                                                           (uint32_t *)ctx->tmaps.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    hb_scan_up_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>((const uint32_t *)ctx->tmaps.p, a.ntiles,
+                                                          (uint64_t *)ctx->wmaps.p,
+                                                          (uint64_t *)ctx->cmaps.p);
+    CK(cudaGetLastError());
+    hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
+                                                  (uint64_t *)ctx->cprefix.p, misc_words(ctx));
+    CK(cudaGetLastError());
+    if (d_map)
+        CK(cudaMemcpyAsync(d_map, misc_words(ctx), 32 * sizeof(uint64_t), cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->have_map = true;
+    ctx->map_ntiles = a.ntiles;
+    ctx->map_ncta = ncta;
+    ctx->map_wpt = WPT;
+    return HB_OK;
+}
+
+template <int WPT>
+static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a,
+                       const uint64_t *d_entry_base, void *d_out, uint64_t out_capacity) {
+    const uint32_t ncta = ctx->map_ncta;
+    uint64_t *misc = misc_words(ctx);
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    hb_scan_down_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
+        (const uint32_t *)ctx->tmaps.p, a.ntiles, (const uint64_t *)ctx->wmaps.p,
+        (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
+        (uint64_t *)ctx->tile_base.p, misc + 32);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    uint32_t stage = stage_bytes_for(WPT, cb->lut.minlen);
+    size_t smem = emit_smem_bytes<WPT>(a.w1, stage);
+    int grid = 1, rc;
+    if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
+    hb_emit_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
+        a, (const uint16_t *)ctx->subs.p, (const uint8_t *)ctx->tile_entry.p,
+        (const uint64_t *)ctx->tile_base.p, (uint8_t *)d_out, out_capacity, stage,
+        (uint32_t *)(misc + 36));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    return HB_OK;
+}
+
+static int prepare_misc(hb_ctx *ctx) {
+    int rc = ensure(ctx, ctx->misc, 64 * sizeof(uint64_t));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 64 * sizeof(uint64_t), ctx->stream));
+    return HB_OK;
+}
+
+extern "C" int hb_shard_map(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                            uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
+                            uint64_t *d_map) {
+    hb_stream_args a;
+    int rc = make_args(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, &a);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = prepare_misc(ctx))) return rc;
+    ctx->have_map = false;
+    /* per-step event set: a slot of the timing ring while one is armed */
+    if (ctx->tim_ev && ctx->tim_n < ctx->tim_cap) ctx->ev = ctx->tim_ev + (size_t)ctx->tim_n++ * HB_NEV;
+    else ctx->ev = ctx->ev0;
+    if (a.ntiles == 0) {
+        /* empty shard: identity map (entry e -> exit e, 0 symbols) */
+        uint64_t ident[32];
+        for (int e = 0; e < 32; e++) ident[e] = (uint64_t)e;
+        CK(cudaMemcpyAsync(ctx->misc.p, ident, sizeof(ident), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (d_map)
+            CK(cudaMemcpyAsync(d_map, ctx->misc.p, sizeof(ident), cudaMemcpyDeviceToDevice, ctx->stream));
+        for (int i = 0; i < HB_NEV; i++) CK(cudaEventRecord(ctx->ev[i], ctx->stream));
+        ctx->have_map = true;
+        ctx->map_ntiles = 0;
+        ctx->map_ncta = 0;
+        ctx->map_wpt = ctx->wpt;
+        return HB_OK;
+    }
+    switch (ctx->wpt) {
+    case 4: return launch_map<4>(ctx, a, d_map);
+    case 8: return launch_map<8>(ctx, a, d_map);
+    case 16: return launch_map<16>(ctx, a, d_map);
+    }
+    return HB_ERR_ARG;
+}
+
+extern "C" int hb_shard_compose(hb_ctx *ctx, const uint64_t *d_all_maps, int n_ranks, int rank,
+                                uint64_t *d_entry_base) {
+    if (!ctx || !d_all_maps || !d_entry_base || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    hb_compose_kernel<<<1, 32, 0, ctx->stream>>>(d_all_maps, n_ranks, rank, d_entry_base);
+    CK(cudaGetLastError());
+    return HB_OK;
+}
+
+static int finish_result(hb_ctx *ctx, uint32_t ntiles, uint32_t launches, hb_result *res) {
+    uint64_t *misc = misc_words(ctx);
+    CK(cudaMemcpyAsync(ctx->h_res, misc + 32, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(res, 0, sizeof(*res));
+    res->n_symbols = ctx->h_res[0];
+    res->exit_offset = (uint32_t)ctx->h_res[1];
+    res->entry_offset = (uint32_t)ctx->h_res[2];
+    res->out_base = ctx->h_res[3];
+    res->launches = launches;
+    res->tiles = ntiles;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) res->ms_sync = ms;
+    float s1 = 0, s2 = 0;
+    cudaEventElapsedTime(&s1, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&s2, ctx->ev[2], ctx->ev[3]);
+    res->ms_scan = s1 + s2;
+    if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) res->ms_emit = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]) == cudaSuccess) res->ms_total = ms;
+    cudaGetLastError();
+    if ((uint32_t)ctx->h_res[4] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
+    return HB_OK;
+}
+
+extern "C" int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                             uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
+                             const uint64_t *d_entry_base, void *d_out, uint64_t out_capacity,
+                             hb_result *res) {
+    hb_stream_args a;
+    int rc = make_args(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, &a);
+    if (rc) return rc;
+    if (!ctx->have_map || ctx->map_ntiles != a.ntiles || ctx->map_wpt != ctx->wpt)
+        return HB_ERR_STATE;
+    if (!d_out && out_capacity) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t launches = 0;
+    if (a.ntiles == 0) {
+        /* result = entry/base passthrough, zero symbols */
+        if (res) {
+            uint64_t eb[2] = {0, 0};
+            if (d_entry_base) {
+                CK(cudaMemcpyAsync(ctx->h_res, d_entry_base, 2 * sizeof(uint64_t),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                eb[0] = ctx->h_res[0]; eb[1] = ctx->h_res[1];
+            }
+            memset(res, 0, sizeof(*res));
+            res->entry_offset = res->exit_offset = (uint32_t)eb[0];
+            res->out_base = eb[1];
+        }
+        return HB_OK;
+    }
+    switch (ctx->wpt) {
+    case 4: rc = launch_emit<4>(ctx, cb, a, d_entry_base, d_out, out_capacity); break;
+    case 8: rc = launch_emit<8>(ctx, cb, a, d_entry_base, d_out, out_capacity); break;
+    case 16: rc = launch_emit<16>(ctx, cb, a, d_entry_base, d_out, out_capacity); break;
+    default: rc = HB_ERR_ARG;
+    }
+    if (rc) return rc;
+    launches = 5;
+    if (res) return finish_result(ctx, a.ntiles, launches, res);
+    return HB_OK;
+}
+
+extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                                uint64_t comp_bytes, uint64_t bits, void *d_out,
+                                uint64_t out_capacity, hb_result *res) {
+    hb_result local;
+    if (!res) res = &local;
+    int rc = hb_shard_map(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr);
+    if (rc) return rc;
+    return hb_shard_emit(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr, d_out, out_capacity, res);
+}
+
+extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
+                              const uint8_t *data, uint64_t bits, uint8_t *out,
+                              uint64_t out_capacity, hb_result *res) {
+    if (!ctx || !tree || (!data && bits) || (!out && out_capacity)) return HB_ERR_ARG;
+    hb_result local;
+    if (!res) res = &local;
+    CK(cudaSetDevice(ctx->device));
+    hb_codebook *cb = nullptr;
+    int rc = hb_codebook_create(ctx, tree, nodes, &cb);
+    if (rc) return rc;
+    const uint64_t nbytes = (bits + 7) / 8;
+    const uint64_t padded = (nbytes + 15) & ~15ull;
+    do {
+        if ((rc = ensure(ctx, ctx->d_comp, padded + 16))) break;
+        if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) break;
+        cudaError_t e = cudaSuccess;
+        if (nbytes) e = cudaMemcpyAsync(ctx->d_comp.p, data, nbytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync((uint8_t *)ctx->d_comp.p + nbytes, 0, padded + 16 - nbytes, ctx->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "upload"); break; }
+        rc = hb_decode_device(ctx, cb, ctx->d_comp.p, padded + 16, bits, ctx->d_out.p, out_capacity, res);
+        if (rc) break;
+        if (res->n_symbols) {
+            e = cudaMemcpyAsync(out, ctx->d_out.p, res->n_symbols, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "download"); break; }
+        }
+    } while (0);
+    hb_codebook_destroy(cb);
+    return rc;
+}
+
+/* used by hb_gen.cu (setup-only generator) to run on the context's device/stream */
+extern "C" int hb_gen_ctx_stream(hb_ctx *ctx, int *device, void **stream) {
+    if (!ctx) return HB_ERR_ARG;
+    *device = ctx->device;
+    *stream = (void *)ctx->stream;
+    return HB_OK;
+}
+
+/* ---- per-step phase timing over many steps (bench) -------------------------
+ * hb_ctx_timing_begin arms a ring of max_steps event sets; every following
+ * hb_shard_map/hb_shard_emit pair records into the next set without any host
+ * synchronisation.  hb_ctx_timing_collect synchronises the stream and returns
+ * the summed CUDA-event milliseconds {sync, scan(+exchange), emit, total}. */
+extern "C" int hb_ctx_timing_begin(hb_ctx *ctx, int max_steps) {
+    if (!ctx || max_steps < 0 || max_steps > 4096) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (max_steps > ctx->tim_cap) {
+        cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->tim_ev, sizeof(cudaEvent_t) * (size_t)max_steps * HB_NEV);
+        if (!ne) return HB_ERR_NOMEM;
+        ctx->tim_ev = ne;
+        for (int i = ctx->tim_cap * HB_NEV; i < max_steps * HB_NEV; i++) CK(cudaEventCreate(&ctx->tim_ev[i]));
+        ctx->tim_cap = max_steps;
+    }
+    ctx->tim_n = 0;
+    ctx->ev = ctx->ev0;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_timing_collect(hb_ctx *ctx, double ms[4], int *steps) {
+    if (!ctx || !ms) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.0;
+    for (int k = 0; k < ctx->tim_n; k++) {
+        cudaEvent_t *e = ctx->tim_ev + (size_t)k * HB_NEV;
+        float a = 0, b = 0, c = 0, d = 0, t = 0;
+        CK(cudaEventElapsedTime(&a, e[0], e[1]));
+        CK(cudaEventElapsedTime(&b, e[1], e[2]));
+        CK(cudaEventElapsedTime(&c, e[2], e[3]));
+        CK(cudaEventElapsedTime(&d, e[3], e[4]));
+        CK(cudaEventElapsedTime(&t, e[0], e[4]));
+        ms[0] += a; ms[1] += b + c; ms[2] += d; ms[3] += t;
+    }
+    if (steps) *steps = ctx->tim_n;
+    ctx->tim_n = ctx->tim_cap;   /* disarm until the next begin */
+    ctx->ev = ctx->ev0;
+    return HB_OK;
+}

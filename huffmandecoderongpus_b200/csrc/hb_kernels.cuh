@@ -1,0 +1,440 @@
+/*
+ * hb_kernels.cuh -- the sm_100a decode kernels.
+ *
+ * Functional phases (reference naming in brackets):
+ *   hb_sync_kernel   phase 1+2 inside a tile: every thread decodes the chain of
+ *                    codewords through its own subsequence, neighbouring chains
+ *                    are stitched until all entry offsets agree, and the tile's
+ *                    entry-offset -> (exit offset, symbol count) map is formed
+ *                    [decodeAllBits + makebigtable, fastgpu.cu:46-93, but one
+ *                    probe per CODEWORD of a handful of chains instead of one
+ *                    tree walk per BIT plus log2(n) full-array passes]
+ *   hb_scan_*        composition of the tile maps across the stream: exact
+ *                    entry offset and output base of every tile
+ *                    [calcbitsindex's top-down index broadcast, fastgpu.cu:96-113]
+ *   hb_emit_kernel   decode the now-known chains and write bytes through a
+ *                    shared-memory staging buffer with 16-byte stores
+ *                    [calcresult + findmax, fastgpu.cu:116-138]
+ *
+ * Data layout in HBM: the compressed stream as little-endian u32 words
+ * (16-byte aligned); per subsequence one u16 record (entry offset | count<<5);
+ * per tile one 32 x u32 map; per 32 tiles / per 1024 tiles one 32 x u64 map.
+ */
+#ifndef HB_KERNELS_CUH_
+#define HB_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hb_core.cuh"
+
+#define HB_T 256            /* threads per CTA = subsequences per tile */
+#define HB_SCAN_T 1024      /* threads per CTA of the scan kernels (32 warps x 32 tiles) */
+
+struct hb_stream_args {
+    const uint32_t *words;   /* compressed stream */
+    uint64_t nwords;         /* readable words */
+    uint64_t bits_own;       /* codewords starting before this bit are ours */
+    uint64_t bits_avail;     /* valid bits in words[] (>= bits_own) */
+    uint32_t ntiles;
+    const uint32_t *lut;     /* whole LUT in global memory */
+    uint32_t w1;             /* level-1 width */
+    uint32_t maxlen;         /* number of candidate entry offsets to resolve */
+};
+
+/* level-1 table footprint in shared memory, kept a multiple of 16 bytes */
+__host__ __device__ __forceinline__ uint32_t hb_lut_smem_words(uint32_t w1) {
+    return ((1u << w1) + 3u) & ~3u;
+}
+
+/* device status word bits */
+#define HB_ST_OUTPUT_FULL 1u
+
+template <int WPT>
+__device__ __forceinline__ void hb_load_words(const hb_stream_args &a, uint64_t wbase,
+                                              uint32_t (&w)[WPT + 1]) {
+    if (wbase + WPT + 1 <= a.nwords) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a.words + wbase);
+#pragma unroll
+        for (int v = 0; v < WPT / 4; v++) {
+            uint4 q = __ldg(p + v);
+            w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+        }
+        w[WPT] = __ldg(a.words + wbase + WPT);
+    } else {
+#pragma unroll
+        for (int j = 0; j <= WPT; j++)
+            w[j] = (wbase + j < a.nwords) ? __ldg(a.words + wbase + j) : 0u;
+    }
+}
+
+/* exclusive block scan of one u32 per thread (HB_T threads); returns the prefix,
+ * *total receives the block sum.  s_warp: >= 9 words of shared memory. */
+__device__ __forceinline__ uint32_t hb_block_exscan(uint32_t v, uint32_t *s_warp,
+                                                    uint32_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = (lane < HB_T / 32) ? s_warp[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int d = 1; d < HB_T / 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) xi += y;
+        }
+        if (lane < HB_T / 32) s_warp[lane] = xi - x;
+        if (lane == HB_T / 32 - 1) s_warp[HB_T / 32] = xi;
+    }
+    __syncthreads();
+    uint32_t pre = s_warp[wid] + inc - v;
+    *total = s_warp[HB_T / 32];
+    return pre;
+}
+
+/* ------------------------------------------------------------------------- */
+template <int WPT>
+__global__ void __launch_bounds__(HB_T)
+hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t TS = T * S;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *s_lut = smem;
+    uint32_t *s_comp = s_lut + hb_lut_smem_words(a.w1);   /* T*WPT + 4 */
+    uint32_t *s_V = s_comp + T * WPT + 4;         /* WPT*T */
+    uint32_t *s_cs = s_V + WPT * T;               /* T */
+    uint32_t *s_end = s_cs + T;                   /* T */
+    uint32_t *s_warp = s_end + T;                 /* 16 */
+    const int t = threadIdx.x;
+
+    for (uint32_t i = t; i < (1u << a.w1); i += T) s_lut[i] = __ldg(a.lut + i);
+    __syncthreads();
+    hb_lutref lut{s_lut, a.lut, (1u << a.w1) - 1u};
+
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t tile_bit0 = (uint64_t)tile * TS;
+        const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+        uint32_t w[WPT + 1];
+        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+#pragma unroll
+        for (int j = 0; j < WPT; j++) s_comp[t * WPT + j] = w[j];
+        if (t == T - 1) s_comp[T * WPT] = w[WPT];
+
+        const uint32_t lim = sub0 >= a.bits_own ? 0u
+                           : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+
+        /* chain of the guess "a codeword starts at offset 0 of my subsequence" */
+        uint32_t V[WPT];
+        uint32_t e = 0;
+        uint32_t endpos = hb_walk<WPT>(lut, w, lim, 0u, V);
+        s_end[t] = endpos;
+        __syncthreads();
+
+        /* stitch: my true entry is where my left neighbour's chain ends; repeat
+         * until nobody's end position moves (1-3 rounds on self-synchronising
+         * data, at most T rounds in general) */
+        for (;;) {
+            bool changed = false;
+            if (t > 0 && lim > 0) {
+                uint32_t en = (s_end[t - 1] - S) & 31u;
+                if (en != e) {
+                    e = en;
+                    uint32_t np;
+                    if (!hb_rewalk<WPT>(lut, w, lim, e, V, &np) && np != endpos) {
+                        endpos = np;
+                        changed = true;
+                    }
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
+            s_end[t] = endpos;
+            __syncthreads();
+        }
+
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            c += __popc(V[j]);
+            s_V[j * T + t] = V[j];
+        }
+        /* a last codeword that runs past the end of the data is not a symbol */
+        if (c && sub0 + endpos > a.bits_avail) c--;
+        subs[(uint64_t)tile * T + t] = hb_sub_pack(e, c);
+
+        uint32_t C0;
+        uint32_t pre = hb_block_exscan(c, s_warp, &C0);
+        s_cs[t] = pre;
+        __syncthreads();
+
+        /* tile map: hypothesis 0 is the converged chain; hypotheses 1..maxlen-1
+         * are followed by one lane each until they join it */
+        if (t < 32) {
+            const uint64_t own_left = a.bits_own - tile_bit0;   /* tile < ntiles => > 0 */
+            const uint64_t av_left = a.bits_avail - tile_bit0;
+            const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+            const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
+            /* exit of hypothesis 0: end of the last active subsequence's chain */
+            const uint32_t tl = (tile_lim - 1u) / S;
+            const uint32_t X0 = (tl * S + s_end[tl] - tile_lim) & 31u;
+            uint32_t m = hb_map_pack32(X0, C0);
+            if (t > 0 && (uint32_t)t < a.maxlen)
+                m = hb_hyp_walk<WPT, T>(lut, s_comp, s_V, s_cs, C0, X0, tile_lim, avail, (uint32_t)t);
+            tmaps[(uint64_t)tile * 32 + t] = m;
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Map composition.  A warp holds 32 maps in registers (lane l = entry l) and
+ * follows all 32 hypotheses at once with shuffles. */
+
+__device__ __forceinline__ uint64_t hb_shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+/* up-sweep: per warp the composition of its 32 tile maps (wmaps), per CTA the
+ * composition of its 32 warp maps (cmaps) */
+__global__ void __launch_bounds__(HB_SCAN_T)
+hb_scan_up_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
+                  uint64_t *__restrict__ wmaps, uint64_t *__restrict__ cmaps) {
+    __shared__ uint64_t s_w[32][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t gw = (uint64_t)blockIdx.x * 32 + wid;
+    uint32_t reg[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        uint64_t tile = gw * 32 + j;
+        reg[j] = tile < ntiles ? __ldg(tmaps + tile * 32 + lane) : hb_map_pack32(lane, 0);
+    }
+    uint32_t cur = lane, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        uint32_t m = __shfl_sync(0xffffffffu, reg[j], cur);
+        cnt += m >> 8;
+        cur = m & 31u;
+    }
+    uint64_t wm = hb_map_pack64(cur, cnt);
+    wmaps[gw * 32 + lane] = wm;
+    s_w[wid][lane] = wm;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t c2 = lane;
+        uint64_t n2 = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            uint64_t m = s_w[j][c2];
+            n2 += m >> 8;
+            c2 = (uint32_t)m & 31u;
+        }
+        cmaps[(uint64_t)blockIdx.x * 32 + lane] = hb_map_pack64(c2, n2);
+    }
+}
+
+/* top: one warp walks the CTA maps in order; cprefix[c][e] = state of hypothesis
+ * e on entering CTA c; shard_map[e] = state after the last CTA */
+__global__ void __launch_bounds__(32)
+hb_scan_top_kernel(const uint64_t *__restrict__ cmaps, uint32_t ncta,
+                   uint64_t *__restrict__ cprefix, uint64_t *__restrict__ shard_map) {
+    const int lane = threadIdx.x;
+    uint32_t cur = lane;
+    uint64_t cnt = 0;
+    for (uint32_t c0 = 0; c0 < ncta; c0 += 32) {
+        uint64_t reg[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            reg[j] = (c0 + j < ncta) ? __ldg(cmaps + (uint64_t)(c0 + j) * 32 + lane)
+                                     : hb_map_pack64(lane, 0);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (c0 + j < ncta) cprefix[(uint64_t)(c0 + j) * 32 + lane] = hb_map_pack64(cur, cnt);
+            uint64_t m = hb_shfl64(reg[j], cur);
+            cnt += m >> 8;
+            cur = (uint32_t)m & 31u;
+        }
+    }
+    shard_map[lane] = hb_map_pack64(cur, cnt);
+}
+
+/* rank composition after the all-gather: entry offset and output base of this
+ * rank, total symbols of all ranks */
+__global__ void hb_compose_kernel(const uint64_t *__restrict__ all_maps, int n_ranks,
+                                  int rank, uint64_t *__restrict__ entry_base) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t cur = 0;
+    uint64_t base = 0;
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == rank) { entry_base[0] = cur; entry_base[1] = base; }
+        uint64_t m = all_maps[(uint64_t)r * 32 + cur];
+        base += m >> 8;
+        cur = (uint32_t)m & 31u;
+    }
+    entry_base[2] = base;
+}
+
+/* down-sweep: fix the entry offset and output base of every tile.
+ * result[0] = symbols of this shard, [1] = exit offset, [2] = entry, [3] = base */
+__global__ void __launch_bounds__(HB_SCAN_T)
+hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
+                    const uint64_t *__restrict__ wmaps, const uint64_t *__restrict__ cprefix,
+                    const uint64_t *__restrict__ shard_map,
+                    const uint64_t *__restrict__ entry_base,
+                    uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
+                    uint64_t *__restrict__ result) {
+    __shared__ uint32_t s_we[32];
+    __shared__ uint64_t s_wb[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t E = entry_base ? (uint32_t)entry_base[0] & 31u : 0u;
+    const uint64_t B = entry_base ? entry_base[1] : 0ull;
+    const uint64_t cp = __ldg(cprefix + (uint64_t)blockIdx.x * 32 + E);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t sm = shard_map[E];
+        result[0] = sm >> 8;
+        result[1] = sm & 31u;
+        result[2] = E;
+        result[3] = B;
+    }
+    if (wid == 0) {
+        uint64_t reg[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            reg[j] = __ldg(wmaps + ((uint64_t)blockIdx.x * 32 + j) * 32 + lane);
+        uint32_t cur = (uint32_t)cp & 31u;
+        uint64_t b = B + (cp >> 8);
+        uint32_t my_e = 0;
+        uint64_t my_b = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (lane == j) { my_e = cur; my_b = b; }
+            uint64_t m = hb_shfl64(reg[j], cur);
+            b += m >> 8;
+            cur = (uint32_t)m & 31u;
+        }
+        s_we[lane] = my_e;
+        s_wb[lane] = my_b;
+    }
+    __syncthreads();
+    const uint64_t gw = (uint64_t)blockIdx.x * 32 + wid;
+    uint32_t reg[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        uint64_t tile = gw * 32 + j;
+        reg[j] = tile < ntiles ? __ldg(tmaps + tile * 32 + lane) : hb_map_pack32(lane, 0);
+    }
+    uint32_t cur = s_we[wid];
+    uint64_t b = s_wb[wid];
+    uint32_t my_e = 0;
+    uint64_t my_b = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (lane == j) { my_e = cur; my_b = b; }
+        uint32_t m = __shfl_sync(0xffffffffu, reg[j], cur);
+        b += m >> 8;
+        cur = m & 31u;
+    }
+    const uint64_t tile = gw * 32 + lane;
+    if (tile < ntiles) {
+        tile_entry[tile] = (uint8_t)my_e;
+        tile_base[tile] = my_b;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+struct hb_stage_sink {
+    uint8_t *p;
+    __device__ __forceinline__ void operator()(uint32_t n, uint32_t sym) const {
+        p[n] = (uint8_t)sym;
+    }
+};
+
+template <int WPT>
+__global__ void __launch_bounds__(HB_T)
+hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
+               const uint8_t *__restrict__ tile_entry, const uint64_t *__restrict__ tile_base,
+               uint8_t *__restrict__ out, uint64_t out_capacity, uint32_t stage_bytes,
+               uint32_t *__restrict__ status) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t TS = T * S;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *s_lut = smem;
+    uint32_t *s_comp = s_lut + hb_lut_smem_words(a.w1);  /* T*WPT + 4 */
+    uint32_t *s_warp = s_comp + T * WPT + 4;          /* 16 */
+    uint16_t *s_sub = reinterpret_cast<uint16_t *>(s_warp + 16);   /* T u16 = T/2 words */
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16 + T / 2);  /* stage_bytes, 16-aligned */
+    const int t = threadIdx.x;
+
+    for (uint32_t i = t; i < (1u << a.w1); i += T) s_lut[i] = __ldg(a.lut + i);
+    __syncthreads();
+    hb_lutref lut{s_lut, a.lut, (1u << a.w1) - 1u};
+
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t tile_bit0 = (uint64_t)tile * TS;
+        const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+        const uint32_t E = tile_entry[tile];
+        const uint64_t B = tile_base[tile];
+        uint32_t w[WPT + 1];
+        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+        uint16_t sub = subs[(uint64_t)tile * T + t];
+
+        if (E != 0) {   /* block-uniform: the stored records assume entry offset 0 */
+#pragma unroll
+            for (int j = 0; j < WPT; j++) s_comp[t * WPT + j] = w[j];
+            if (t == T - 1) s_comp[T * WPT] = w[WPT];
+            s_sub[t] = sub;
+            __syncthreads();
+            if (t == 0) {
+                const uint64_t own_left = a.bits_own - tile_bit0;
+                const uint64_t av_left = a.bits_avail - tile_bit0;
+                const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+                const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
+                hb_fix_entries<WPT, T>(lut, s_comp, s_sub, tile_lim, avail, E);
+            }
+            __syncthreads();
+            sub = s_sub[t];
+        }
+        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        uint32_t nk;
+        const uint32_t o = hb_block_exscan(c, s_warp, &nk);
+
+        const uint32_t lim = sub0 >= a.bits_own ? 0u
+                           : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+        const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B) & 15u);
+        hb_stage_sink sink{s_out + al + o};
+        if (c) hb_walk_emit<WPT>(lut, w, lim, e, sink);
+        __syncthreads();
+
+        /* staging -> global: s_out[al + i] -> out[B + i], 16-byte vectors aligned
+         * in both spaces, partial first/last vectors byte-wise */
+        if (B + nk > out_capacity) {
+            if (t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
+        } else {
+            uint8_t *gbase = out + B - al;     /* 16-byte aligned */
+            const uint32_t endb = al + nk;
+            const uint32_t nvec = (endb + 15u) >> 4;
+            for (uint32_t v = t; v < nvec; v += T) {
+                const uint32_t b0 = v << 4;
+                if (b0 >= al && b0 + 16u <= endb) {
+                    *reinterpret_cast<uint4 *>(gbase + b0) =
+                        *reinterpret_cast<const uint4 *>(s_out + b0);
+                } else {
+                    const uint32_t lo = b0 < al ? al : b0;
+                    const uint32_t hi = b0 + 16u < endb ? b0 + 16u : endb;
+                    for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
+                }
+            }
+        }
+        __syncthreads();
+        (void)stage_bytes;
+    }
+}
+
+#endif /* HB_KERNELS_CUH_ */

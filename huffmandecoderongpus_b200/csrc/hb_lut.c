@@ -1,0 +1,193 @@
+/*
+ * hb_lut.c -- Huffman tree -> multi-level lookup table (host, plain C).
+ *
+ * The reference decodes by walking the node array bit by bit on the device
+ * (framework/fastgpu.cu:46-66) and only has single-level 2^height tables on
+ * the CPU (framework/mainrun.c:142-195, capped at height 23 by mask2).  Here
+ * the first level is W1 <= 11 bits wide so that it fits shared memory; longer
+ * codes chain through sub-tables of at most W2 bits (world192 has 20-bit
+ * codes, the adversarial config up to 32).
+ */
+#include "hb_lut.h"
+#include "hb_format.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define HB_W1_DEFAULT 11
+#define HB_W2_DEFAULT 10
+#define HB_MAX_ENTRIES (1u << 18)
+
+typedef struct builder {
+    const hb_node *tree;
+    int nodes;
+    int w1, w2;
+    uint32_t *ent;
+    uint32_t n, cap;
+    int32_t *sub_of_node; /* memoised sub-table base per internal node, -1 = none */
+    uint8_t *height;      /* subtree height per node */
+    int err;
+} builder;
+
+static int is_leaf(const hb_node *n) { return n->izero == -1 && n->ione == -1; }
+
+/* iterative validation: every reachable node is a full internal node or a leaf,
+ * indices in range, no node reached twice (=> a tree, no cycles), depth <= 32 */
+static int validate(const hb_node *tree, int nodes, uint8_t *height,
+                    uint32_t *maxlen, uint32_t *minlen, uint32_t *nleaves) {
+    if (nodes < 3 || !tree) return HB_ERR_TREE;
+    if (is_leaf(&tree[0])) return HB_ERR_TREE;
+    uint8_t *seen = (uint8_t *)calloc((size_t)nodes, 1);
+    int32_t *stack = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)nodes + 16);
+    uint8_t *depth = (uint8_t *)calloc((size_t)nodes, 1);
+    int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)nodes);
+    if (!seen || !stack || !depth || !order) {
+        free(seen); free(stack); free(depth); free(order);
+        return HB_ERR_NOMEM;
+    }
+    int rc = HB_OK, sp = 0, no = 0;
+    uint32_t mx = 0, mn = 0xffffffffu, nl = 0;
+    stack[sp++] = 0;
+    seen[0] = 1;
+    while (sp > 0 && rc == HB_OK) {
+        int32_t v = stack[--sp];
+        order[no++] = v;
+        const hb_node *nd = &tree[v];
+        if (is_leaf(nd)) {
+            uint32_t d = depth[v];
+            if (d > mx) mx = d;
+            if (d < mn) mn = d;
+            nl++;
+            continue;
+        }
+        int32_t ch[2] = { nd->izero, nd->ione };
+        for (int k = 0; k < 2; k++) {
+            int32_t c = ch[k];
+            if (c <= 0 || c >= nodes || seen[c]) { rc = HB_ERR_TREE; break; }
+            if (depth[v] + 1 > HB_MAX_CODELEN) { rc = HB_ERR_CODELEN; break; }
+            seen[c] = 1;
+            depth[c] = (uint8_t)(depth[v] + 1);
+            stack[sp++] = c;
+        }
+    }
+    if (rc == HB_OK) {
+        /* heights bottom-up: children appear after parents in `order` */
+        for (int i = no - 1; i >= 0; i--) {
+            int32_t v = order[i];
+            if (is_leaf(&tree[v])) height[v] = 0;
+            else {
+                uint8_t a = height[tree[v].izero], b = height[tree[v].ione];
+                height[v] = (uint8_t)(1 + (a > b ? a : b));
+            }
+        }
+        *maxlen = mx; *minlen = mn; *nleaves = nl;
+    }
+    free(seen); free(stack); free(depth); free(order);
+    return rc;
+}
+
+static uint32_t alloc_table(builder *b, int width) {
+    uint32_t need = 1u << width;
+    if (b->n + need > HB_MAX_ENTRIES) { b->err = HB_ERR_NOMEM; return 0; }
+    if (b->n + need > b->cap) {
+        uint32_t nc = b->cap ? b->cap : 4096;
+        while (nc < b->n + need) nc *= 2;
+        uint32_t *ne = (uint32_t *)realloc(b->ent, sizeof(uint32_t) * nc);
+        if (!ne) { b->err = HB_ERR_NOMEM; return 0; }
+        b->ent = ne;
+        b->cap = nc;
+    }
+    uint32_t base = b->n;
+    b->n += need;
+    return base;
+}
+
+static uint32_t build_table(builder *b, int32_t root, int width);
+
+/* fill all slots of table `base` (index width `width`) whose low `depth` bits
+ * equal `prefix` with what the walk from `node` finds */
+static void fill(builder *b, uint32_t base, int width, int32_t node, int depth,
+                 uint32_t prefix) {
+    if (b->err) return;
+    const hb_node *nd = &b->tree[node];
+    if (is_leaf(nd)) {
+        uint32_t e = (uint32_t)depth | ((uint32_t)nd->sym << 8);
+        for (uint32_t i = prefix; i < (1u << width); i += (1u << depth))
+            b->ent[base + i] = e;
+        return;
+    }
+    if (depth == width) {
+        int nw = b->height[node] < b->w2 ? b->height[node] : b->w2;
+        uint32_t sub = (b->sub_of_node[node] >= 0) ? (uint32_t)b->sub_of_node[node]
+                                                  : build_table(b, node, nw);
+        if (b->err) return;
+        b->ent[base + prefix] = HB_LUT_LINK | (uint32_t)width | ((uint32_t)nw << 8) |
+                                (sub << 13);
+        return;
+    }
+    fill(b, base, width, nd->izero, depth + 1, prefix);
+    fill(b, base, width, nd->ione, depth + 1, prefix | (1u << depth));
+}
+
+static uint32_t build_table(builder *b, int32_t root, int width) {
+    uint32_t base = alloc_table(b, width);
+    if (b->err) return 0;
+    b->sub_of_node[root] = (int32_t)base;
+    fill(b, base, width, root, 0, 0);
+    return base;
+}
+
+static void collect_codes(const hb_node *tree, int32_t node, int depth,
+                          uint32_t bits, hb_lut *out, uint8_t *have) {
+    const hb_node *nd = &tree[node];
+    if (is_leaf(nd)) {
+        if (!have[nd->sym]) {
+            have[nd->sym] = 1;
+            out->code[nd->sym] = bits;
+            out->codelen[nd->sym] = (uint8_t)depth;
+        }
+        return;
+    }
+    collect_codes(tree, nd->izero, depth + 1, bits, out, have);
+    collect_codes(tree, nd->ione, depth + 1, bits | (depth < 32 ? (1u << depth) : 0u), out, have);
+}
+
+int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out) {
+    if (!out) return HB_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    if (nodes > (1 << 20)) return HB_ERR_TREE;
+    builder b;
+    memset(&b, 0, sizeof(b));
+    b.tree = tree;
+    b.nodes = nodes;
+    b.height = (uint8_t *)calloc((size_t)(nodes > 0 ? nodes : 1), 1);
+    if (!b.height) return HB_ERR_NOMEM;
+    int rc = validate(tree, nodes, b.height, &out->maxlen, &out->minlen, &out->n_leaves);
+    if (rc != HB_OK) { free(b.height); return rc; }
+    b.w1 = (w1_max > 0 ? w1_max : HB_W1_DEFAULT);
+    b.w2 = (w2_max > 0 ? w2_max : HB_W2_DEFAULT);
+    if (b.w1 > 13) b.w1 = 13;
+    if (b.w2 > 12) b.w2 = 12;
+    if ((uint32_t)b.w1 > out->maxlen) b.w1 = (int)out->maxlen;
+    b.sub_of_node = (int32_t *)malloc(sizeof(int32_t) * (size_t)nodes);
+    if (!b.sub_of_node) { free(b.height); return HB_ERR_NOMEM; }
+    for (int i = 0; i < nodes; i++) b.sub_of_node[i] = -1;
+    build_table(&b, 0, b.w1);
+    free(b.sub_of_node);
+    free(b.height);
+    if (b.err) { free(b.ent); return b.err; }
+    out->entries = b.ent;
+    out->n_entries = b.n;
+    out->w1 = (uint32_t)b.w1;
+    uint8_t have[256];
+    memset(have, 0, sizeof(have));
+    collect_codes(tree, 0, 0, 0, out, have);
+    return HB_OK;
+}
+
+void hb_lut_free(hb_lut *lut) {
+    if (!lut) return;
+    free(lut->entries);
+    lut->entries = NULL;
+    lut->n_entries = 0;
+}

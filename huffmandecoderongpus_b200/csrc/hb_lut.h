@@ -1,0 +1,41 @@
+/*
+ * hb_lut.h -- host-side code-table construction: Huffman tree (the reference's
+ * node array, framework/huffdata.h:12-16) -> multi-level lookup table consumed
+ * by the kernels (entry format in hb_core.cuh).  Plain C.
+ */
+#ifndef HB_LUT_H_
+#define HB_LUT_H_
+
+#include <stdint.h>
+#include "huffb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same layout as the reference's struct HuffNode (12 bytes, 3 bytes padding) */
+typedef hb_node_abi hb_node;
+
+typedef struct hb_lut {
+    uint32_t *entries;   /* level 1 first (1 << w1 entries), then sub-tables */
+    uint32_t  n_entries;
+    uint32_t  w1;        /* level-1 index width in bits */
+    uint32_t  maxlen;    /* longest codeword (reference tableHeight)   */
+    uint32_t  minlen;    /* shortest codeword (reference tableMinDepth) */
+    uint32_t  n_leaves;
+    /* canonical per-symbol code (first leaf found for each symbol), used by the
+     * bundled encoder: code bits LSB-first in stream order */
+    uint32_t  code[256];
+    uint8_t   codelen[256];
+} hb_lut;
+
+/* Validate the tree and build the table.  w1_max/w2_max cap the widths of the
+ * first and of every deeper level (0 = defaults 11 / 10).
+ * Returns 0 or a negative HB_ERR_* code (include/huffb200.h). */
+int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out);
+void hb_lut_free(hb_lut *lut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

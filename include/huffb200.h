@@ -1,0 +1,194 @@
+/*
+ * huffb200.h -- C ABI of libhuffb200.so, the B200 (sm_100a) speculative
+ * parallel Huffman decoder that replaces the reference's GPU decode backend.
+ *
+ * Plain pointers and sizes only; callable from C without CUDA headers.  The
+ * reference conflates allocation, transfer, decode and download in one call
+ * (framework/fastgpu.cu:140-332, timed as a whole by framework/decodeUtil.c:41-43);
+ * this ABI separates them so a harness can report device time on resident
+ * data AND end-to-end time:
+ *
+ *   reference interface replaced                        entry point here
+ *   --------------------------------------------------  -----------------------------
+ *   fastgpuApproach(cd, out, NULL)   fastgpu.cu:140      b200Approach (b200approach.h)
+ *     cudaMalloc/cudaMemcpy tree+data fastgpu.cu:196-201  hb_codebook_create, hb_decode_host
+ *     decodeAllBits..calcresult       fastgpu.cu:214-305  hb_decode_device
+ *     (no multi-GPU in the reference)                     hb_shard_map / _compose / _emit
+ *   loadHuffFile                     huffdata.c:27-68    hb_huff_load / hb_huff_free
+ *   tableHeight / tableMinDepth      huffdata.c:224,272  hb_codebook_info
+ *
+ * Every function returns HB_OK (0) or a negative HB_ERR_* code; nothing here
+ * prints or exits (the reference's print-and-exit behaviour, fastgpu.cu:16-31,
+ * is reproduced only at the approach boundary, b200Approach).
+ * There is no CPU fallback: without a CUDA device hb_ctx_create fails.
+ */
+#ifndef HUFFB200_H_
+#define HUFFB200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK               0
+#define HB_ERR_CUDA        -1  /* CUDA runtime error (hb_last_error has the text) */
+#define HB_ERR_TREE        -2  /* malformed tree: bad child index, half-leaf, cycle, leaf root */
+#define HB_ERR_CODELEN     -3  /* a codeword is longer than 32 bits */
+#define HB_ERR_ARG         -4  /* bad argument (NULL, misaligned device pointer, sizes) */
+#define HB_ERR_NOMEM       -5
+#define HB_ERR_OUTPUT_FULL -6  /* decoded length exceeds out_capacity (nothing past it is written) */
+#define HB_ERR_IO          -7
+#define HB_ERR_FORMAT      -8  /* not a HUFF / HUF8 file */
+#define HB_ERR_STATE       -9  /* call order (e.g. hb_shard_emit without hb_shard_map) */
+
+/* Tree node: identical layout to the reference's struct HuffNode
+ * (framework/huffdata.h:12-16): node 0 is the root, leaf <=> izero == ione == -1. */
+typedef struct hb_node_abi {
+    uint8_t sym;
+    int32_t izero;
+    int32_t ione;
+} hb_node_abi;
+
+typedef struct hb_ctx hb_ctx;           /* one device + one stream + scratch */
+typedef struct hb_codebook hb_codebook; /* lookup tables resident on the device */
+
+typedef struct hb_result {
+    uint64_t n_symbols;   /* decoded bytes written by this call */
+    uint64_t out_base;    /* index of this shard's first symbol in the whole stream */
+    uint32_t exit_offset; /* bit offset, past the end of the owned range, of the next codeword */
+    uint32_t entry_offset;/* bit offset of the first owned codeword */
+    uint32_t launches;    /* kernels launched by this call */
+    uint32_t tiles;
+    float ms_total;       /* CUDA-event time of all kernels of this call */
+    float ms_sync;        /* phase 1: per-subsequence chains + tile maps */
+    float ms_scan;        /* phase 2: map composition across tiles */
+    float ms_emit;        /* phase 3: decode + coalesced write */
+} hb_result;
+
+const char *hb_strerror(int code);
+const char *hb_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+/* cuda_stream: a cudaStream_t created by the caller (e.g. torch's current
+ * stream) or NULL to let the context own a non-blocking stream. */
+int  hb_ctx_create(int device, void *cuda_stream, hb_ctx **ctx);
+void hb_ctx_destroy(hb_ctx *ctx);
+const char *hb_last_error(const hb_ctx *ctx);
+/* words_per_thread: 4, 8 or 16 32-bit words per subsequence (0 = default);
+ * ctas_per_sm: persistent CTAs per SM (0 = occupancy-derived). */
+int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
+int  hb_ctx_sync(hb_ctx *ctx);
+/* Phase timing over many steps without host synchronisation in between:
+ * _begin arms a ring of max_steps CUDA-event sets (one per following
+ * hb_shard_map + hb_shard_emit pair); _collect synchronises the stream and
+ * returns the summed milliseconds ms[0..3] = {sync, scan (+ exchange between
+ * the two calls), emit, total} and the number of steps recorded. */
+int  hb_ctx_timing_begin(hb_ctx *ctx, int max_steps);
+int  hb_ctx_timing_collect(hb_ctx *ctx, double ms[4], int *steps);
+int  hb_device_info(hb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                    uint64_t *total_mem);
+
+/* ---- codebook ------------------------------------------------------------ */
+int  hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
+                        hb_codebook **cb);
+void hb_codebook_destroy(hb_codebook *cb);
+int  hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,
+                      uint32_t *w1, uint32_t *n_entries);
+
+/* ---- whole stream, device-resident input and output ----------------------- */
+/* d_comp: device pointer, 16-byte aligned, comp_bytes >= ceil(bits/8) readable
+ * bytes.  d_out: device pointer with out_capacity bytes.  Runs on the
+ * context's stream, synchronises it, and fills *res. */
+int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                     uint64_t comp_bytes, uint64_t bits, void *d_out,
+                     uint64_t out_capacity, hb_result *res);
+
+/* ---- byte-range shards (multi-GPU or streaming) --------------------------- */
+/* A shard owns the codewords that START in its first bits_own bits; d_comp
+ * holds bits_avail >= bits_own bits (the surplus is the halo into the next
+ * shard, >= 32 bits unless the stream ends).  hb_shard_map leaves, in device
+ * memory d_map (32 x u64), the shard's transfer map: entry e ->
+ * (symbol count << 8) | exit offset.  Asynchronous on the context's stream. */
+int hb_shard_map(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                 uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
+                 uint64_t *d_map);
+/* d_all_maps: n_ranks x 32 x u64 (the all-gathered maps, rank-major, device).
+ * Composes ranks 0..rank-1 from entry offset 0 and writes
+ * d_entry_base[0] = this rank's entry offset, [1] = its output base,
+ * [2] = total symbols of all ranks.  Asynchronous. */
+int hb_shard_compose(hb_ctx *ctx, const uint64_t *d_all_maps, int n_ranks,
+                     int rank, uint64_t *d_entry_base);
+/* Second half: fix every tile's entry offset / output base from
+ * d_entry_base[0..1] (NULL = entry 0, base 0) and write the shard's symbols to
+ * d_out[0 .. n).  Must follow hb_shard_map on the same context with the same
+ * stream arguments.  Synchronises and fills *res when res != NULL. */
+int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
+                  uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
+                  const uint64_t *d_entry_base, void *d_out,
+                  uint64_t out_capacity, hb_result *res);
+
+/* ---- host buffers (what the approach call does) --------------------------- */
+/* Upload tree + data, decode, download.  data must have >= ceil(bits/8) bytes.
+ * Device buffers are cached in the context and grow on demand. */
+int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
+                   const uint8_t *data, uint64_t bits, uint8_t *out,
+                   uint64_t out_capacity, hb_result *res);
+
+/* ---- .huff container ------------------------------------------------------ */
+/* "HUFF" (reference framework/huffdata.c:27-68: BE i32 nodes, bits, usize) and
+ * "HUF8" (this repo: BE u64 bits, usize) files.  data gets >= 16 zero bytes of
+ * padding.  Free with hb_huff_free. */
+typedef struct hb_huff_file {
+    int32_t      nodes;
+    int32_t      wide;    /* 1 = HUF8 */
+    uint64_t     bits;
+    uint64_t     usize;
+    hb_node_abi *tree;
+    uint8_t     *data;
+} hb_huff_file;
+int  hb_huff_load(const char *path, hb_huff_file *out);
+int  hb_huff_save(const char *path, const hb_huff_file *in, int wide);
+void hb_huff_free(hb_huff_file *f);
+
+/* ---- bundled synthetic-stream generator (the reference has no
+ * encoder).  Symbol i of a stream is a pure function of (model, seed, i). ---- */
+#define HB_MODEL_ENGLISH   0  /* order-0 byte histogram of the reference's files/bible.txt */
+#define HB_MODEL_FIBONACCI 1  /* 256 symbols, Fibonacci-skewed, 20 < max code length <= 32 */
+#define HB_MODEL_DNA       2  /* 4 equiprobable symbols: all codes 2 bits, never self-synchronises */
+#define HB_MODEL_UNIFORM8  3  /* 8 equiprobable symbols: all codes 3 bits (adversarial for sync) */
+
+typedef struct hb_model {
+    int32_t     nodes;           /* Huffman tree in the reference's node format */
+    hb_node_abi tree[511];
+    uint32_t    cum[256];        /* sampling thresholds over the nsyms present symbols, in symbol
+                                    order: draw u32 u, pick the largest k < nsyms with cum[k] <= u */
+    uint8_t     symtab[256];     /* k -> symbol value */
+    uint32_t    code[256];       /* LSB-first code bits per symbol value */
+    uint8_t     codelen[256];
+    uint32_t    maxlen, minlen, nsyms;
+} hb_model;
+int hb_model_build(int kind, hb_model *m);
+/* CPU generation / encoding (spec of the stream; used for small cases and tests) */
+void     hb_gen_symbols_cpu(const hb_model *m, uint64_t seed, uint64_t first, uint64_t n, uint8_t *out);
+uint64_t hb_encode_bits_cpu(const hb_model *m, const uint8_t *syms, uint64_t n);           /* total bits */
+void     hb_encode_cpu(const hb_model *m, const uint8_t *syms, uint64_t n, uint8_t *out);   /* out zeroed, ceil(bits/8)+8 bytes */
+/* GPU generation / encoding, device-resident: d_comp must hold comp_capacity
+ * zero-initialisable bytes; *bits_out receives the stream length. */
+int hb_gen_encode_device(hb_ctx *ctx, const hb_model *m, uint64_t seed,
+                         uint64_t first_symbol, uint64_t n_symbols,
+                         void *d_comp, uint64_t comp_capacity, uint64_t *bits_out);
+/* Compare d_out[0..n) with regenerated symbols first_symbol.. ; *mismatches out. */
+int hb_gen_verify_device(hb_ctx *ctx, const hb_model *m, uint64_t seed,
+                         uint64_t first_symbol, uint64_t n_symbols,
+                         const void *d_out, uint64_t *mismatches);
+/* Exact encoded length, in bits, of symbols [first, first + n) (device-side count). */
+int hb_gen_count_bits_device(hb_ctx *ctx, const hb_model *m, uint64_t seed,
+                             uint64_t first_symbol, uint64_t n_symbols,
+                             uint64_t *bits_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUFFB200_H_ */

@@ -1,0 +1,78 @@
+"""ctypes driver of tests/emul/emul.cpp (CPU emulation of the CUDA tile algorithm).
+TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import huffmandecoderongpus_b200 as hb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emul", "emul.cpp")
+SO = os.path.join(ROOT, "tests", "emul", "libemul.so")
+CSRC = os.path.join(ROOT, "huffmandecoderongpus_b200", "csrc")
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "tiles", "rounds_total", "rounds_max", "probes_walk", "probes_rewalk", "probes_hyp",
+        "probes_fix", "probes_emit", "warp_iters_walk", "warp_iters_rewalk", "warp_iters_hyp",
+        "warp_iters_emit", "hyp_unmerged", "tiles_entry_nonzero", "long_probes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [SRC, os.path.join(CSRC, "hb_core.cuh"), os.path.join(CSRC, "hb_format.h")]
+        if (not os.path.exists(SO)) or any(os.path.getmtime(SO) < os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC,
+                                   SRC, "-o", SO])
+        L = C.CDLL(SO)
+        L.emul_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                               C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                               C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                               C.c_void_p, C.POINTER(Stats)]
+        _lib = L
+    return _lib
+
+
+def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
+    """compressed bytes -> little-endian u32 words (zero padded)"""
+    n = (nbytes + 3) // 4
+    buf = np.zeros(n * 4, dtype=np.uint8)
+    buf[:nbytes] = data[:nbytes]
+    return buf.view("<u4").copy()
+
+
+def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=True,
+        out_capacity=None, out_offset=0):
+    """Returns (out bytes, shard_map[32], result[4], stats dict, rc)."""
+    cap = int(out_capacity if out_capacity is not None else bits_own + 64)
+    raw = np.zeros(cap + 64 + out_offset, dtype=np.uint8)
+    out = raw[out_offset:]
+    smap = np.zeros(32, dtype=np.uint64)
+    res = np.zeros(4, dtype=np.uint64)
+    st = Stats()
+    ent = np.ascontiguousarray(lut["entries"], dtype=np.uint32)
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"], words.ctypes.data,
+                        words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
+                        out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st))
+    return out, smap, res, st.as_dict(), rc
+
+
+def decode(stream, wpt=4, T=256, lut=None, **kw):
+    """Whole-stream emulated decode of an oracle_lib.Stream / hb.HuffFile."""
+    lut = lut or hb.build_lut(stream.tree)
+    w = words_of(stream.data, (stream.bits + 7) // 8)
+    out, smap, res, st, rc = run(lut, w, stream.bits, stream.bits, wpt, T, **kw)
+    return out[: int(res[0])], st, rc

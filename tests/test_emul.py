@@ -1,0 +1,166 @@
+"""CPU emulation of the CUDA tile algorithm (tests/emul/emul.cpp, which drives the
+very device functions of csrc/hb_core.cuh) checked against the oracle.  This is
+how the algorithm is validated in the GPU-less build container; the -m gpu
+tests repeat the same cases on the real kernels."""
+import numpy as np
+import pytest
+
+import emul_lib as E
+import oracle_lib as O
+import huffmandecoderongpus_b200 as hb
+
+SHAPES_BIG = [(4, 256), (8, 256), (16, 256)]
+SHAPES_SMALL = [(1, 4), (2, 8), (4, 32), (1, 64)]
+
+
+def _stream(name):
+    p = O.corpus_path(name)
+    if p is None:
+        pytest.skip(f"{name} corpus not present")
+    return O.load_huff(p)
+
+
+@pytest.mark.parametrize("name", list(O.CORPORA))
+@pytest.mark.parametrize("shape", SHAPES_BIG)
+def test_corpora(name, shape):
+    st = _stream(name)
+    got, stats, rc = E.decode(st, *shape)
+    assert rc == 0
+    assert got.size == st.usize
+    assert O.sha256(got) == O.CORPORA[name][2]
+
+
+@pytest.mark.parametrize("name", ["hello", "paper1", "news"])
+@pytest.mark.parametrize("shape", SHAPES_SMALL)
+def test_small_tiles_many_boundaries(name, shape):
+    st = _stream(name)
+    got, stats, rc = E.decode(st, *shape)
+    assert rc == 0 and np.array_equal(got, O.simple_decode(st))
+    if name != "hello":
+        assert stats["tiles_entry_nonzero"] > 0  # the entry fix-up path really ran
+
+
+@pytest.mark.parametrize("shape", [(4, 256), (1, 4)])
+def test_prefix_sweep(shape):
+    # reference graphtest / setTargetSizes, framework/mainrun.c:361-410
+    st = _stream("paper1")
+    lut = hb.build_lut(st.tree)
+    for target in list(range(1, 70)) + list(range(10000, 266692, 31337)) + [st.bits - 1, st.bits]:
+        bits, usize = O.prefix_sizes(st, target)
+        w = E.words_of(st.data, (bits + 7) // 8)
+        out, _, res, _, rc = E.run(lut, w, bits, bits, *shape)
+        assert rc == 0 and int(res[0]) == usize, target
+        assert np.array_equal(out[:usize], O.simple_decode(st, bits=bits)), target
+
+
+@pytest.mark.parametrize("shape", [(4, 256), (2, 8)])
+def test_stream_cut_inside_a_codeword(shape):
+    # the serial oracle emits a symbol only on reaching a leaf: a trailing partial
+    # codeword yields nothing (framework/mainrun.c:44-53)
+    st = _stream("paper1")
+    lut = hb.build_lut(st.tree)
+    for bits in [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 1000, 4095, 4096, 4097, 32767, 32768, 32769,
+                 100001, st.bits - 3]:
+        want = O.simple_decode(st, bits=bits)
+        w = E.words_of(st.data, (bits + 7) // 8)
+        # bits past the cut are garbage (the rest of the real stream), not zeros
+        w2 = E.words_of(st.data, min(st.nbytes, (bits + 7) // 8 + 8))
+        for words in (w, w2):
+            out, _, res, _, rc = E.run(lut, words, bits, bits, *shape)
+            assert rc == 0 and int(res[0]) == want.size, bits
+            assert np.array_equal(out[: want.size], want), bits
+
+
+def test_empty_stream():
+    st = _stream("hello")
+    lut = hb.build_lut(st.tree)
+    out, smap, res, _, rc = E.run(lut, np.zeros(4, np.uint32), 0, 0)
+    assert rc == 0 and int(res[0]) == 0
+    assert [int(m) for m in smap] == list(range(32))  # identity map
+
+
+def _compose(maps, rank):
+    cur, base = 0, 0
+    for r in range(rank):
+        m = int(maps[r][cur])
+        base += m >> 8
+        cur = m & 31
+    return cur, base
+
+
+@pytest.mark.parametrize("name,cuts", [
+    ("paper1", [16, 4096, 4112, 20000]),
+    ("news", [8192 * 3, 8192 * 17]),
+    ("kjv", [1024 * 1024, 2 * 1024 * 1024 + 16]),
+    ("ecoli", [500000 - 500000 % 16]),
+])
+@pytest.mark.parametrize("shape", [(4, 256), (2, 8)])
+def test_byte_range_shards(name, cuts, shape):
+    """Multi-GPU decomposition: contiguous 16-byte-aligned byte ranges, one map
+    per shard, host-side composition (what hb_shard_compose does), independent
+    emit of every shard into its own buffer."""
+    if shape == (2, 8) and name in ("kjv", "ecoli"):
+        pytest.skip("small shape only on small corpora")
+    st = _stream(name)
+    want = O.simple_decode(st)
+    lut = hb.build_lut(st.tree)
+    bounds = [0] + cuts + [st.nbytes]
+    shards = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        last = b == st.nbytes
+        bits_own = (st.bits - 8 * a) if last else 8 * (b - a)
+        halo_end = min(st.nbytes, b + 8)
+        bits_avail = bits_own if last else min(st.bits - 8 * a, 8 * (halo_end - a))
+        words = E.words_of(st.data[a:], halo_end - a)
+        shards.append((words, bits_own, bits_avail))
+    maps = []
+    for words, bo, ba in shards:
+        _, smap, _, _, rc = E.run(lut, words, bo, ba, *shape, emit=False)
+        assert rc == 0
+        maps.append(smap)
+    pieces = []
+    for r, (words, bo, ba) in enumerate(shards):
+        entry, base = _compose(maps, r)
+        out, _, res, _, rc = E.run(lut, words, bo, ba, *shape, entry=entry, base=0, out_offset=r % 5)
+        assert rc == 0
+        assert int(res[2]) == entry
+        pieces.append(out[: int(res[0])])
+        assert base == sum(p.size for p in pieces[:-1])
+    got = np.concatenate(pieces)
+    assert got.size == want.size and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind,n", [(hb.MODEL_ENGLISH, 300000), (hb.MODEL_FIBONACCI, 300000),
+                                    (hb.MODEL_DNA, 100000), (hb.MODEL_UNIFORM8, 20000)])
+@pytest.mark.parametrize("shape", [(4, 256), (8, 256), (1, 4)])
+def test_synthetic_models(kind, n, shape):
+    m = hb.Model(kind)
+    if kind == hb.MODEL_FIBONACCI:
+        assert 20 < m.maxlen <= 32  # the adversarial tree needs a multi-level table
+    f, syms = m.huff_file_cpu(seed=0x48554646, n=n)
+    lut = hb.build_lut(f.tree)
+    assert lut["maxlen"] == m.maxlen and lut["minlen"] == m.minlen
+    got, stats, rc = E.decode(f, *shape, lut=lut)
+    assert rc == 0 and np.array_equal(got, syms)
+    # and the oracle agrees with the generator
+    st = O.Stream(f.tree, f.data, f.bits, f.usize)
+    assert np.array_equal(O.simple_decode(st), syms)
+
+
+def test_output_too_small_is_reported():
+    st = _stream("paper1")
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    _, _, _, _, rc = E.run(lut, w, st.bits, st.bits, out_capacity=st.usize - 1)
+    assert rc == -6
+
+
+def test_output_alignment_offsets():
+    st = _stream("paper1")
+    want = O.simple_decode(st)
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    for off in range(0, 16):
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, out_offset=off)
+        assert rc == 0 and np.array_equal(out[: want.size], want)
+        assert not out[want.size:].any()  # nothing written past the end

@@ -1,0 +1,246 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI
+(libhuffb200.so), against the CPU oracle, the reference's SHA-256 digests and
+size-independent properties (encode -> decode round trips at full size).
+Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import huffmandecoderongpus_b200 as hb
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+SEED = 0x48554646  # "HUFF"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(0)
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ctx(dev):
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    yield c
+    c.close()
+
+
+def _stream(name):
+    p = O.corpus_path(name)
+    if p is None:
+        pytest.skip(f"{name} corpus not present")
+    return hb.HuffFile.load(p)
+
+
+def _to_dev(data: np.ndarray, nbytes: int, dev, extra=0):
+    """compressed bytes -> CUDA uint8 tensor, zero padded to a multiple of 16"""
+    n = (nbytes + 15) // 16 * 16 + 16 + extra
+    t = torch.zeros(n, dtype=torch.uint8, device=dev)
+    t[:nbytes] = torch.from_numpy(np.ascontiguousarray(data[:nbytes])).to(dev)
+    return t
+
+
+def _decode_dev(ctx, cb, f, dev, bits=None, cap=None, out_offset=0):
+    bits = f.bits if bits is None else bits
+    comp = _to_dev(f.data, (bits + 7) // 8, dev)
+    cap = (f.usize if cap is None else cap)
+    raw = torch.zeros(cap + 64 + out_offset, dtype=torch.uint8, device=dev)
+    out = raw[out_offset:]
+    res = hb.decode_device(ctx, cb, comp.data_ptr(), comp.numel(), bits, out.data_ptr(), cap)
+    return out[: res["n_symbols"]].cpu().numpy(), res, raw
+
+
+@pytest.mark.parametrize("name", list(O.CORPORA))
+def test_corpora_host_buffers(ctx, name):
+    """BASELINE configs 1-3: every shipped corpus through hb_decode_host (upload,
+    decode, download), byte-exact against the reference's own output digest."""
+    f = _stream(name)
+    out = np.zeros(f.usize + 3, dtype=np.uint8)
+    res = hb.decode_host(ctx, f.tree, f.data, f.bits, out[: f.usize])
+    assert res["n_symbols"] == f.usize == O.CORPORA[name][4]
+    assert O.sha256(out[: f.usize]) == O.CORPORA[name][2]
+    assert res["launches"] > 0 and res["ms_total"] > 0
+    pt = O.plaintext_path(name)
+    if pt is not None:
+        assert bytes(out[: f.usize]) == open(pt, "rb").read()
+
+
+@pytest.mark.parametrize("name", ["hello", "paper1", "news", "book2", "kjv"])
+def test_approach_drop_in(name):
+    """The bigtable suite (framework/mainrun.c:541-588) calling convention:
+    reference-layout structs, zeroed usize+3 output, 1 checked + repeated runs
+    (framework/decodeUtil.c:30-70)."""
+    f = _stream(name)
+    st = O.Stream(f.tree, f.data, f.bits, f.usize)
+    want = O.simple_decode(st)
+    for rep in range(3):
+        got = hb.b200_approach(f.tree, f.data, f.bits, f.usize)
+        assert np.array_equal(got, want)
+    assert hb.lib().b200ApproachLastSymbols() == f.usize
+    assert hb.lib().b200ApproachLastDeviceMs() > 0
+
+
+@pytest.mark.parametrize("wpt", [4, 8, 16])
+@pytest.mark.parametrize("name", ["hello", "paper1", "world192", "kjv", "ecoli"])
+def test_device_resident_all_shapes(dev, name, wpt):
+    f = _stream(name)
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
+    cb = hb.Codebook(c, f.tree)
+    got, res, _ = _decode_dev(c, cb, f, dev)
+    assert got.size == f.usize and O.sha256(got) == O.CORPORA[name][2]
+    cb.close()
+    c.close()
+
+
+def test_prefix_sweep(ctx, dev):
+    # reference graphtest / setTargetSizes, framework/mainrun.c:361-410
+    f = _stream("paper1")
+    st = O.Stream(f.tree, f.data, f.bits, f.usize)
+    cb = hb.Codebook(ctx, f.tree)
+    for target in list(range(1, 40)) + list(range(10000, f.bits, 31337)) + [f.bits - 1, f.bits]:
+        bits, usize = O.prefix_sizes(st, target)
+        got, res, _ = _decode_dev(ctx, cb, f, dev, bits=bits, cap=usize)
+        assert res["n_symbols"] == usize, target
+        assert np.array_equal(got, O.simple_decode(st, bits=bits)), target
+
+
+def test_cut_inside_codeword_and_empty(ctx, dev):
+    f = _stream("paper1")
+    st = O.Stream(f.tree, f.data, f.bits, f.usize)
+    cb = hb.Codebook(ctx, f.tree)
+    for bits in [0, 1, 2, 3, 31, 32, 33, 127, 128, 129, 4095, 4096, 4097, 32767, 32768, 32769, 100001]:
+        want = O.simple_decode(st, bits=bits)
+        got, res, _ = _decode_dev(ctx, cb, f, dev, bits=bits, cap=want.size + 8)
+        assert res["n_symbols"] == want.size and np.array_equal(got, want), bits
+
+
+def test_output_alignment_and_no_overrun(ctx, dev):
+    f = _stream("paper1")
+    want = O.simple_decode(O.Stream(f.tree, f.data, f.bits, f.usize))
+    cb = hb.Codebook(ctx, f.tree)
+    for off in (0, 1, 3, 7, 8, 15):
+        got, res, raw = _decode_dev(ctx, cb, f, dev, out_offset=off)
+        assert np.array_equal(got, want)
+        host = raw.cpu().numpy()
+        assert not host[:off].any() and not host[off + want.size:].any()
+
+
+def test_output_too_small_and_bad_args(ctx, dev):
+    f = _stream("paper1")
+    cb = hb.Codebook(ctx, f.tree)
+    with pytest.raises(hb.HuffError) as e:
+        _decode_dev(ctx, cb, f, dev, cap=f.usize - 1)
+    assert e.value.code == -6
+    comp = _to_dev(f.data, f.nbytes, dev, extra=16)
+    out = torch.zeros(f.usize + 64, dtype=torch.uint8, device=dev)
+    with pytest.raises(hb.HuffError) as e:   # misaligned compressed pointer
+        hb.decode_device(ctx, cb, comp.data_ptr() + 4, comp.numel() - 4, f.bits, out.data_ptr(), f.usize)
+    assert e.value.code == -4
+    with pytest.raises(hb.HuffError) as e:   # fewer readable bytes than the stream needs
+        hb.decode_device(ctx, cb, comp.data_ptr(), f.nbytes - 1, f.bits, out.data_ptr(), f.usize)
+    assert e.value.code == -4
+    bad = f.tree.copy()
+    bad["ione"][0] = -1                      # half-leaf root
+    with pytest.raises(hb.HuffError) as e:
+        hb.Codebook(ctx, bad)
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("name,nshards", [("paper1", 3), ("kjv", 2), ("kjv", 8), ("ecoli", 4)])
+def test_byte_range_shards_on_one_gpu(dev, name, nshards):
+    """The multi-GPU decomposition with every 'rank' run on cuda:0: one context
+    per rank, maps gathered by concatenation, hb_shard_compose, independent emit."""
+    f = _stream(name)
+    want = O.simple_decode(O.Stream(f.tree, f.data, f.bits, f.usize))
+    per = (f.nbytes // nshards) // 16 * 16
+    bounds = [r * per for r in range(nshards)] + [f.nbytes]
+    stream = torch.cuda.current_stream().cuda_stream
+    ctxs = [hb.Context(0, stream=stream) for _ in range(nshards)]
+    cbs = [hb.Codebook(c, f.tree) for c in ctxs]
+    all_maps = torch.zeros(nshards * 32, dtype=torch.int64, device=dev)
+    shards = []
+    for r in range(nshards):
+        a, b = bounds[r], bounds[r + 1]
+        last = r == nshards - 1
+        bits_own = f.bits - 8 * a if last else 8 * (b - a)
+        halo_end = min(f.nbytes, b + 16)
+        bits_avail = bits_own if last else min(f.bits - 8 * a, 8 * (halo_end - a))
+        comp = _to_dev(f.data[a:], halo_end - a, dev)
+        shards.append((comp, bits_own, bits_avail))
+        hb.shard_map(ctxs[r], cbs[r], comp.data_ptr(), comp.numel(), bits_own, bits_avail,
+                     all_maps[r * 32:].data_ptr())
+    pieces, base_expect = [], 0
+    for r, (comp, bo, ba) in enumerate(shards):
+        eb = torch.zeros(4, dtype=torch.int64, device=dev)
+        hb.shard_compose(ctxs[r], all_maps.data_ptr(), nshards, r, eb.data_ptr())
+        out = torch.zeros(want.size + 64, dtype=torch.uint8, device=dev)
+        res = hb.shard_emit(ctxs[r], cbs[r], comp.data_ptr(), comp.numel(), bo, ba, eb.data_ptr(),
+                            out.data_ptr(), want.size)
+        # each rank writes its own slice starting at 0; out_base says where it belongs
+        assert res["out_base"] == base_expect
+        assert int(eb[2]) == want.size
+        base_expect += res["n_symbols"]
+        pieces.append(out[: res["n_symbols"]].cpu().numpy())
+    got = np.concatenate(pieces)
+    assert got.size == want.size and np.array_equal(got, want)
+    for cb in cbs:
+        cb.close()
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.parametrize("kind,n", [(hb.MODEL_ENGLISH, 1 << 20), (hb.MODEL_FIBONACCI, 1 << 20),
+                                    (hb.MODEL_DNA, 1 << 18), (hb.MODEL_UNIFORM8, 1 << 15)])
+def test_gpu_encoder_matches_cpu_encoder_and_oracle(ctx, dev, kind, n):
+    """The bundled generator: GPU-built stream == CPU-built stream bit for bit, the
+    oracle decodes it back to the generated symbols, and so does the GPU decoder."""
+    m = hb.Model(kind)
+    f, syms = m.huff_file_cpu(SEED, n)
+    comp = torch.zeros((f.nbytes + 15) // 16 * 16 + 32, dtype=torch.uint8, device=dev)
+    bits = hb.gen_encode_device(ctx, m, SEED, 0, n, comp.data_ptr(), comp.numel())
+    assert bits == f.bits == hb.gen_count_bits_device(ctx, m, SEED, 0, n)
+    assert np.array_equal(comp[: f.nbytes].cpu().numpy(), f.data[: f.nbytes])
+    assert np.array_equal(O.simple_decode(O.Stream(f.tree, f.data, f.bits, f.usize)), syms)
+    cb = hb.Codebook(ctx, m.tree)
+    out = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    res = hb.decode_device(ctx, cb, comp.data_ptr(), comp.numel(), bits, out.data_ptr(), n)
+    assert res["n_symbols"] == n
+    assert np.array_equal(out[:n].cpu().numpy(), syms)
+    assert hb.gen_verify_device(ctx, m, SEED, 0, n, out.data_ptr()) == 0
+    out[n // 2] ^= 1
+    assert hb.gen_verify_device(ctx, m, SEED, 0, n, out.data_ptr()) == 1
+
+
+@pytest.mark.parametrize("kind,log2n,wpt", [(hb.MODEL_ENGLISH, 30, 4), (hb.MODEL_ENGLISH, 30, 8),
+                                            (hb.MODEL_FIBONACCI, 30, 4), (hb.MODEL_FIBONACCI, 32, 8)])
+def test_full_size_round_trip(dev, kind, log2n, wpt):
+    """BASELINE configs 4/5 at full single-GPU size: generate + encode on the
+    device (> 2^31 bits: the 64-bit path), decode, and compare every byte with
+    the regenerated symbols; the CPU oracle checks a prefix."""
+    n = 1 << log2n
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
+    m = hb.Model(kind)
+    bits = hb.gen_count_bits_device(c, m, SEED, 0, n)
+    assert bits > 2 ** 31
+    nbytes = (bits + 7) // 8
+    comp = torch.zeros((nbytes + 15) // 16 * 16 + 32, dtype=torch.uint8, device=dev)
+    assert hb.gen_encode_device(c, m, SEED, 0, n, comp.data_ptr(), comp.numel()) == bits
+    cb = hb.Codebook(c, m.tree)
+    out = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    res = hb.decode_device(c, cb, comp.data_ptr(), comp.numel(), bits, out.data_ptr(), n)
+    assert res["n_symbols"] == n
+    assert hb.gen_verify_device(c, m, SEED, 0, n, out.data_ptr()) == 0
+    # oracle on the first 2^22 symbols
+    k = 1 << 22
+    kb = hb.gen_count_bits_device(c, m, SEED, 0, k)
+    host = comp[: (kb + 7) // 8 + 16].cpu().numpy()
+    st = O.Stream(m.tree, np.concatenate([host, np.zeros(16, np.uint8)]), kb, k)
+    assert np.array_equal(O.simple_decode(st), out[:k].cpu().numpy())
+    cb.close()
+    c.close()
+    del comp, out
+    torch.cuda.empty_cache()
