@@ -237,7 +237,11 @@ class Model:
 class Context:
     def __init__(self, device=0, stream=None, words_per_thread=0, ctas_per_sm=0):
         self.h = C.c_void_p()
-        _check(lib().hb_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)),
+        # stream: a cudaStream_t handle as an int; 0 (torch's default stream) is passed as
+        # cudaStreamLegacy (0x1), None lets the context own a non-blocking stream
+        if stream is not None and int(stream) == 0:
+            stream = 1
+        _check(lib().hb_ctx_create(device, C.c_void_p(stream) if stream is not None else None, C.byref(self.h)),
                "hb_ctx_create (a CUDA device is required; there is no CPU fallback)")
         self.device = device
         if words_per_thread or ctas_per_sm:

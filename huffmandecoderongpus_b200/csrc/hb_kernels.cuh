@@ -308,7 +308,7 @@ hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
         for (int j = 0; j < 32; j++)
             reg[j] = __ldg(wmaps + ((uint64_t)blockIdx.x * 32 + j) * 32 + lane);
         uint32_t cur = (uint32_t)cp & 31u;
-        uint64_t b = B + (cp >> 8);
+        uint64_t b = cp >> 8;      /* offsets are local to this shard's output buffer */
         uint32_t my_e = 0;
         uint64_t my_b = 0;
 #pragma unroll

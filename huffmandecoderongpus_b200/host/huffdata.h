@@ -63,12 +63,13 @@ void freeUnCompressedData(struct UnCompressedData *ucd);
 void clearUnCompressedData(struct UnCompressedData *ucd);
 int compareUnCompressedData(struct UnCompressedData *a, struct UnCompressedData *b);
 struct TestData *loadTestData(const char *filename, const char *name);
-struct TestData *loadTestDataDigest(const char *hufffile, const char *name);
+
 void freeTestData(struct TestData *td);
 void infoCompressedData(struct CompressedData *cd);
 void infoTestData(struct TestData *td);
 int tableHeight(struct HuffNode *tree, int r);
 int tableMinDepth(struct HuffNode *tree, int r);
 int treeSize(struct HuffNode *tree, int r);
+int digestUnCompressedData(struct UnCompressedData *u, char hex[65]);
 
 #endif

@@ -219,7 +219,7 @@ struct Emul {
         result[0] = shard_map[E] >> 8; result[1] = shard_map[E] & 31u; result[2] = E; result[3] = B;
         for (uint32_t cta = 0; cta < ncta; cta++) {
             uint64_t cp = cprefix[(uint64_t)cta * 32 + E];
-            uint32_t cur = (uint32_t)cp & 31u; uint64_t b = B + (cp >> 8);
+            uint32_t cur = (uint32_t)cp & 31u; uint64_t b = cp >> 8;
             uint32_t we[32]; uint64_t wb[32];
             for (int j = 0; j < 32; j++) {
                 we[j] = cur; wb[j] = b;
