@@ -549,3 +549,39 @@ extern "C" int hb_ctx_timing_collect(hb_ctx *ctx, double ms[4], int *steps) {
     ctx->ev = ctx->ev0;
     return HB_OK;
 }
+
+/* ---- plain device memory for C hosts ----------------------------------------- */
+extern "C" int hb_dev_alloc(hb_ctx *ctx, uint64_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr) return HB_ERR_ARG;
+    *d_ptr = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); *d_ptr = nullptr; return HB_ERR_NOMEM; }
+    CK(cudaMemsetAsync(*d_ptr, 0, bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+extern "C" int hb_dev_free(hb_ctx *ctx, void *d_ptr) {
+    if (!ctx) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (d_ptr) CK(cudaFree(d_ptr));
+    return HB_OK;
+}
+
+extern "C" int hb_dev_upload(hb_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!d_dst || !h_src))) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}
+
+extern "C" int hb_dev_download(hb_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!h_dst || !d_src))) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
+}

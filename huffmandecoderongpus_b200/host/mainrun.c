@@ -1,0 +1,202 @@
+/*
+ * mainrun.c -- C harness with the shape of the reference's framework/mainrun.c:
+ * an approach table (newDecoder, :480-501), datasets loaded by name (:505-509),
+ * one positional test name, "name dataset time" lines (evalandshow, :412-420).
+ *
+ * Differences the survey asked for: the test names kjv,
+ * ecoli, world192 and bible exist; corpora without a shipped plaintext are
+ * checked by SHA-256; the data directory is an argument instead of a
+ * hard-coded ../../files; device time and GB/s are appended to each line.
+ *
+ *   HuffFramework <test> [files-dir]
+ *   tests: hello paper1 news book2 kjv ecoli world192 bible bigtable all
+ *          quickgraph graph synth1g synthfib
+ *
+ * The GPU approach (b200Approach) is always registered.  The CPU baselines
+ * (the oracle's restatement of simpleDecode / jumptableApproach) are only
+ * linked with -DWITH_ORACLE_BASELINES (make HuffFrameworkBaselines): the
+ * product binary has no CPU decode path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200approach.h"
+#include "decodeUtil.h"
+#include "huffb200.h"
+#include "huffdata.h"
+
+#ifdef WITH_ORACLE_BASELINES
+#include "huff_oracle.h"
+static void simpleDecode(struct CompressedData *cd, struct UnCompressedData *u, void *p) {
+    (void)p;
+    ora_simple_decode((const ora_node *)cd->tree, cd->data, (uint64_t)cd->bits, u->data,
+                      (uint64_t)u->uncompressedsize);
+}
+static void jumptableApproach(struct CompressedData *cd, struct UnCompressedData *u, void *p) {
+    ora_jumptable_decode((const ora_node *)cd->tree, cd->nodes, cd->data, (uint64_t)cd->bits,
+                         *(int *)p, u->data, (uint64_t)u->uncompressedsize);
+}
+#endif
+
+struct dataset {
+    const char *name, *file, *sha256;   /* sha256 of the reference's own decode */
+    struct TestData *td;
+};
+
+static struct dataset g_sets[] = {
+    { "hello", "hello", "a591a6d40bf420404a011733cfb7b190d62c65bf0bcda32b57b277d9ad9f146e", NULL },
+    { "paper1", "paper1", "8d9c42d9fa58b5bce1a8b5fae3cc27c9eb7cc7a032bc12a633d44e816497e143", NULL },
+    { "news", "news", "7f0482f9774681429eb7021050c17966f6acf19450e170de6611e1ed953d42e8", NULL },
+    { "book2", "book2", "c8538730cf2ce6a243acf3eb299c43d619b5c695d892f4884df796c13081fdf8", NULL },
+    { "kjv", "kjv.txt", "e4e21579f6360b35e66dc97b67cd732a3f759623e41e4e077bec039eeb79fd0a", NULL },
+    { "ecoli", "E.coli", "9125dfd87315961ef4286f3856098069e050cc3a2abe65735fe43e69d1996f40", NULL },
+    { "world192", "world192.txt", "1aebdc97d29904b25791da9aa32be90b69d7da6dc0ac9b95512ed27ed40d2112", NULL },
+    { "bible", "bible.txt", "4e0a7e8dff7d9c82dbded57305c0ca3cdd3c4ca014db27121782fe9710f4723f", NULL },
+};
+#define NSETS ((int)(sizeof(g_sets) / sizeof(g_sets[0])))
+
+static const char *g_dir = "../../oracle/_ref/files";
+
+static struct dataset *get_set(const char *name) {
+    for (int i = 0; i < NSETS; i++) {
+        if (strcmp(g_sets[i].name, name)) continue;
+        if (!g_sets[i].td) {
+            char path[1024];
+            snprintf(path, sizeof(path), "%s/%s", g_dir, g_sets[i].file);
+            g_sets[i].td = loadTestData(path, g_sets[i].name);
+            if (!g_sets[i].td) {
+                fprintf(stderr, "error exit: cannot load %s.huff\n", path);
+                exit(1);
+            }
+        }
+        return &g_sets[i];
+    }
+    return NULL;
+}
+
+static void evalandshow(struct decoder *d, struct dataset *s, int withcheck) {
+    struct evalresult r = evaluate_ex(d, s->td, withcheck, s->sha256);
+    const double out_b = (double)s->td->cd->uncompressedsize;
+    const double in_b = (double)((s->td->cd->bits + 7) / 8);
+    if (d->paramdata != NULL)   /* the reference prints seconds in this form, mainrun.c:413-415 */
+        printf("%17s %8s  %2d %.9f", d->name, s->name, *(int *)d->paramdata, r.min_seconds);
+    else
+        printf("%17s %8s     %.9f ms", d->name, s->name, r.min_seconds * 1000.0);
+    printf("   | %.4f GB/s out, %.4f GB/s in (wall)", out_b / r.min_seconds / 1e9, in_b / r.min_seconds / 1e9);
+    if (r.min_device_ms >= 0)
+        printf(", device %.4f ms = %.3f GB/s out", r.min_device_ms, out_b / (r.min_device_ms * 1e-3) / 1e9);
+    printf(" [%s]\n", r.checked == 1 ? "bytes ok" : r.checked == 2 ? "sha256 ok" : "unchecked");
+    fflush(stdout);
+}
+
+/* reference graphtest + setTargetSizes (framework/mainrun.c:361-410): decode
+ * prefixes of growing length that end on a codeword boundary */
+static void graphtest(struct decoder *d, struct dataset *s, int incs) {
+    struct CompressedData cut = *s->td->cd;
+    struct UnCompressedData plain;
+    struct TestData red;
+    red.name = s->td->name;
+    red.cd = &cut;
+    red.ucd = s->td->ucd ? &plain : NULL;
+    /* one serial pass records, for every target, the last whole-codeword boundary */
+    const struct CompressedData *cd = s->td->cd;
+    int node = 0, nsym = 0, lastok = 0, next = incs;
+    for (int pos = 0; pos < cd->bits; pos++) {
+        if (pos == next) {
+            cut.bits = lastok + 1;
+            cut.uncompressedsize = nsym;
+            if (s->td->ucd) { plain.data = s->td->ucd->data; plain.uncompressedsize = nsym; }
+            struct evalresult r = evaluate_ex(d, &red, s->td->ucd != NULL, NULL);
+            printf("%8d  %.9f  %.6f\n", next, r.min_seconds, r.min_device_ms);
+            fflush(stdout);
+            next += incs;
+        }
+        int bit = (cd->data[pos >> 3] >> (pos & 7)) & 1;
+        node = bit ? cd->tree[node].ione : cd->tree[node].izero;
+        if (cd->tree[node].izero == -1 && cd->tree[node].ione == -1) { nsym++; node = 0; lastok = pos; }
+    }
+}
+
+/* BASELINE.json configs 4/5 from the C side: build the stream on the device with
+ * the bundled generator, decode it resident, verify every byte on the device */
+static void synth(int kind, unsigned log2n, const char *label) {
+    hb_ctx *ctx = NULL;
+    hb_model *m = (hb_model *)malloc(sizeof(*m));
+    int rc = hb_ctx_create(0, NULL, &ctx);
+    if (rc || !m) { printf("hb_ctx_create: %s\n", hb_strerror(rc)); exit(-1); }
+    if ((rc = hb_model_build(kind, m))) { printf("hb_model_build: %s\n", hb_strerror(rc)); exit(-1); }
+    const uint64_t n = 1ull << log2n, seed = 0x48554646ull;
+    uint64_t bits = 0, bad = 0;
+    void *d_comp = NULL, *d_out = NULL;
+    hb_gen_count_bits_device(ctx, m, seed, 0, n, &bits);
+    uint64_t cap = ((bits + 7) / 8 + 15) / 16 * 16 + 64;
+    if (hb_dev_alloc(ctx, cap, &d_comp) || hb_dev_alloc(ctx, n + 64, &d_out)) { printf("device alloc failed\n"); exit(-1); }
+    if ((rc = hb_gen_encode_device(ctx, m, seed, 0, n, d_comp, cap, &bits))) { printf("encode: %s\n", hb_strerror(rc)); exit(-1); }
+    hb_codebook *cb = NULL;
+    if ((rc = hb_codebook_create(ctx, m->tree, m->nodes, &cb))) { printf("codebook: %s\n", hb_strerror(rc)); exit(-1); }
+    hb_result res;
+    double best = -1;
+    for (int i = 0; i < 5; i++) {
+        if ((rc = hb_decode_device(ctx, cb, d_comp, cap, bits, d_out, n, &res))) {
+            printf("decode: %s (%s)\n", hb_strerror(rc), hb_last_error(ctx));
+            exit(-1);
+        }
+        if (best < 0 || res.ms_total < best) best = res.ms_total;
+    }
+    hb_gen_verify_device(ctx, m, seed, 0, n, d_out, &bad);
+    printf("%17s %8s     %.9f ms   | %.3f GB/s out, %.3f GB/s in (device), bits %llu, max code length %u, "
+           "symbols %llu, mismatches %llu\n", "b200", label, best, (double)n / (best * 1e-3) / 1e9,
+           (double)((bits + 7) / 8) / (best * 1e-3) / 1e9, (unsigned long long)bits, m->maxlen,
+           (unsigned long long)res.n_symbols, (unsigned long long)bad);
+    if (bad || res.n_symbols != n) { fprintf(stderr, "problem with : b200\n"); exit(1); }
+    hb_codebook_destroy(cb);
+    hb_dev_free(ctx, d_comp);
+    hb_dev_free(ctx, d_out);
+    hb_ctx_destroy(ctx);
+    free(m);
+}
+
+int main(int argc, char *argv[]) {
+    const char *testname = argc > 1 ? argv[1] : "hello";
+    if (argc > 2) g_dir = argv[2];
+    else if (getenv("HUFF_FILES")) g_dir = getenv("HUFF_FILES");
+    fprintf(stderr, "running test: %s\n", testname);
+
+    struct decoder *b200 = newDecoder(b200Approach, NULL, "b200");
+#ifdef WITH_ORACLE_BASELINES
+    static int jumpbits = 8;
+    struct decoder *simpledec = newDecoder(simpleDecode, NULL, "simpleDecode");
+    struct decoder *jumptable = newDecoder(jumptableApproach, &jumpbits, "jumptableApproach");
+#endif
+    const char *suite_bigtable[] = { "paper1", "hello", "news", "kjv", "book2" };   /* order of mainrun.c:558-562 */
+    const char *suite_all[] = { "hello", "paper1", "news", "book2", "world192", "bible", "kjv", "ecoli" };
+    const char **suite = NULL;
+    int ns = 0;
+    const char *one[1];
+
+    if (!strcmp(testname, "bigtable")) { suite = suite_bigtable; ns = 5; }
+    else if (!strcmp(testname, "all")) { suite = suite_all; ns = 8; }
+    else if (get_set(testname)) { one[0] = testname; suite = one; ns = 1; }
+    else if (!strcmp(testname, "quickgraph")) { graphtest(b200, get_set("paper1"), 10000); }
+    else if (!strcmp(testname, "graph")) { graphtest(b200, get_set("kjv"), 500000); }
+    else if (!strcmp(testname, "synth1g")) { synth(HB_MODEL_ENGLISH, 30, "synth1g"); }
+    else if (!strcmp(testname, "synthfib")) { synth(HB_MODEL_FIBONACCI, 32, "synthfib"); }
+    else { fprintf(stderr, "error exit: unknown test %s\n", testname); return 1; }
+
+    if (suite) {
+        for (int i = 0; i < ns; i++) infoTestData(get_set(suite[i])->td);
+        for (int i = 0; i < ns; i++) evalandshow(b200, get_set(suite[i]), 1);
+#ifdef WITH_ORACLE_BASELINES
+        for (int i = 0; i < ns; i++) evalandshow(simpledec, get_set(suite[i]), 1);
+        for (int i = 0; i < ns; i++) evalandshow(jumptable, get_set(suite[i]), 1);
+#endif
+    }
+    for (int i = 0; i < NSETS; i++) freeTestData(g_sets[i].td);
+    freeDecoder(b200);
+#ifdef WITH_ORACLE_BASELINES
+    freeDecoder(simpledec);
+    freeDecoder(jumptable);
+#endif
+    return 0;
+}

@@ -90,6 +90,13 @@ int  hb_ctx_timing_collect(hb_ctx *ctx, double ms[4], int *steps);
 int  hb_device_info(hb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                     uint64_t *total_mem);
 
+/* Device memory for C hosts that keep streams resident without CUDA headers
+ * (zero-filled, 256-byte aligned).  hb_dev_upload / _download are synchronous. */
+int  hb_dev_alloc(hb_ctx *ctx, uint64_t bytes, void **d_ptr);
+int  hb_dev_free(hb_ctx *ctx, void *d_ptr);
+int  hb_dev_upload(hb_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
+int  hb_dev_download(hb_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
+
 /* ---- codebook ------------------------------------------------------------ */
 int  hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
                         hb_codebook **cb);
