@@ -60,8 +60,9 @@ class ModelC(C.Structure):
 class LutC(C.Structure):
     _fields_ = [("entries", C.POINTER(C.c_uint32)), ("n_entries", C.c_uint32),
                 ("w1", C.c_uint32), ("maxlen", C.c_uint32), ("minlen", C.c_uint32),
-                ("n_leaves", C.c_uint32), ("code", C.c_uint32 * 256),
-                ("codelen", C.c_uint8 * 256)]
+                ("n_leaves", C.c_uint32), ("wf", C.c_uint32),
+                ("stab", C.POINTER(C.c_uint32)), ("etab", C.POINTER(C.c_uint32)),
+                ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256)]
 
 
 class RefCompressedData(C.Structure):
@@ -196,6 +197,9 @@ def build_lut(tree, w1_max=0, w2_max=0):
         return {
             "entries": np.ctypeslib.as_array(lut.entries, shape=(lut.n_entries,)).copy(),
             "w1": lut.w1, "maxlen": lut.maxlen, "minlen": lut.minlen, "n_leaves": lut.n_leaves,
+            "wf": lut.wf,
+            "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
+            "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
     finally:

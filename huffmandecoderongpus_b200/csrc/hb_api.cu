@@ -182,10 +182,16 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
     int rc = hb_lut_build(tree, nodes, 0, 0, &cb->lut);
     if (rc != HB_OK) { delete cb; return rc; }
     cudaSetDevice(ctx->device);
-    size_t bytes = sizeof(uint32_t) * (size_t)cb->lut.n_entries;
+    /* device layout: [single-symbol LUT][S-table][E-table] */
+    const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
+    size_t bytes = sizeof(uint32_t) * (n1 + 2 * nf);
     cudaError_t e = cudaMalloc((void **)&cb->d_lut, bytes);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cb->d_lut, cb->lut.entries, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(cb->d_lut, cb->lut.entries, sizeof(uint32_t) * n1, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cb->d_lut + n1, cb->lut.stab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cb->d_lut + n1 + nf, cb->lut.etab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (cb->d_lut) cudaFree(cb->d_lut);
@@ -217,21 +223,19 @@ extern "C" int hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_
 
 /* ---- launch helpers ------------------------------------------------------ */
 
+/* dynamic shared memory (the fast table is a static 16 KB array in each kernel) */
 template <int WPT>
-static size_t sync_smem_bytes(uint32_t w1) {
-    return sizeof(uint32_t) * ((size_t)hb_lut_smem_words(w1) + HB_T * WPT + 4 +
-                               (size_t)WPT * HB_T + HB_T + HB_T + 16);
+static size_t sync_smem_bytes(uint32_t) {
+    return sizeof(uint32_t) * ((size_t)HB_T * WPT + 4 + (size_t)WPT * HB_T + HB_T + HB_T + 16);
 }
 
-template <int WPT>
-static size_t emit_smem_bytes(uint32_t w1, uint32_t stage_bytes) {
-    return sizeof(uint32_t) * ((size_t)hb_lut_smem_words(w1) + HB_T * WPT + 4 + 16 + HB_T / 2) +
-           stage_bytes;
+static size_t emit_smem_bytes(uint32_t, uint32_t stage_bytes) {
+    return sizeof(uint32_t) * 16 + stage_bytes;
 }
 
 static uint32_t stage_bytes_for(int wpt, uint32_t minlen) {
     /* at most ceil(S / minlen) codewords start in a subsequence; + alignment
-     * shift (<16) + one slack symbol per tile, rounded to 16 */
+     * shift (<16), rounded to 16 */
     uint32_t S = 32u * (uint32_t)wpt;
     uint32_t per = (S + minlen - 1) / minlen;
     uint32_t b = HB_T * per + 16 + 16;
@@ -240,8 +244,8 @@ static uint32_t stage_bytes_for(int wpt, uint32_t minlen) {
 
 template <typename K>
 static int grid_for(hb_ctx *ctx, K kernel, size_t smem, uint32_t ntiles, int *grid) {
-    if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    /* static (16 KB fast table) + dynamic can exceed the 48 KB default: always opt in */
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, HB_T, smem));
     if (occ < 1) {
@@ -274,6 +278,8 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
     a->lut = cb->d_lut;
     a->w1 = cb->lut.w1;
     a->maxlen = cb->lut.maxlen;
+    a->fast = cb->d_lut + cb->lut.n_entries;   /* S-table; the E-table follows it */
+    a->wf = cb->lut.wf;
     return HB_OK;
 }
 
@@ -292,7 +298,7 @@ static int launch_map(hb_ctx *ctx, const hb_stream_args &a, uint64_t *d_map) {
     if ((rc = ensure(ctx, ctx->tile_base, sizeof(uint64_t) * (size_t)a.ntiles))) return rc;
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    size_t smem = sync_smem_bytes<WPT>(a.w1);
+    size_t smem = sync_smem_bytes<WPT>(a.wf);
     int grid = 1;
     if ((rc = grid_for(ctx, hb_sync_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
     hb_sync_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(a, (uint16_t *)ctx->subs.p,
@@ -322,20 +328,28 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
                        const uint64_t *d_entry_base, void *d_out, uint64_t out_capacity) {
     const uint32_t ncta = ctx->map_ncta;
     uint64_t *misc = misc_words(ctx);
+    int rc;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     hb_scan_down_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
         (const uint32_t *)ctx->tmaps.p, a.ntiles, (const uint64_t *)ctx->wmaps.p,
         (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
-        (uint64_t *)ctx->tile_base.p, misc + 32);
+        (uint64_t *)ctx->tile_base.p, misc + 32, a.bits_own, a.bits_avail);
     CK(cudaGetLastError());
+    {   /* re-chain the head of every tile whose true entry offset is not 0 (S-table) */
+        hb_fix_kernel<WPT><<<(a.ntiles + HB_T - 1) / HB_T, HB_T, 0, ctx->stream>>>(
+            a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    hb_stream_args ae = a;
+    ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
     uint32_t stage = stage_bytes_for(WPT, cb->lut.minlen);
-    size_t smem = emit_smem_bytes<WPT>(a.w1, stage);
-    int grid = 1, rc;
+    size_t smem = emit_smem_bytes(a.wf, stage);
+    int grid = 1;
     if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
     hb_emit_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
-        a, (const uint16_t *)ctx->subs.p, (const uint8_t *)ctx->tile_entry.p,
-        (const uint64_t *)ctx->tile_base.p, (uint8_t *)d_out, out_capacity, stage,
+        ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+        (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity,
         (uint32_t *)(misc + 36));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -454,7 +468,7 @@ extern "C" int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_c
     default: rc = HB_ERR_ARG;
     }
     if (rc) return rc;
-    launches = 5;
+    launches = 6;
     if (res) return finish_result(ctx, a.ntiles, launches, res);
     return HB_OK;
 }

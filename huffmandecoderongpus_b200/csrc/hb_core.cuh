@@ -99,148 +99,276 @@ HB_HD uint16_t hb_sub_pack(uint32_t e, uint32_t c) { return (uint16_t)((c << 5) 
 HB_HD uint32_t hb_sub_entry(uint16_t s) { return s & 31u; }
 HB_HD uint32_t hb_sub_count(uint16_t s) { return (uint32_t)s >> 5; }
 
-/* ==== per-thread chain walks over one subsequence ==========================
- * A subsequence is WPT consecutive 32-bit words (S = 32*WPT bits) owned by one
- * thread; w[WPT] is the first word of the next subsequence (a codeword may
- * straddle the boundary by at most 31 bits).  Positions are bit offsets from
- * the start of the subsequence.  lim (0..S) is the number of leading bit
- * positions at which a codeword may START here (S, except where the stream
- * ends inside the subsequence).  V[j] has bit (p & 31) set iff a codeword of
- * the chain starts at position p = 32*j + (p & 31).                          */
+/* ==== word-granular chain walks =============================================
+ * A chain of codewords is followed one 32-bit stream word at a time.  For a
+ * word whose first `bound` bit positions may start a codeword (bound = 32
+ * except where the stream ends) the walk yields
+ *     cnt  = number of codewords of the chain that start in [0, bound)
+ *     land = (first codeword start at or after bound) - bound      (0..31)
+ * Two chains that land at the same offset behind a word are identical from
+ * there on, so "land equals the recorded land" is an exact merge test and the
+ * per-word (land, cnt) records are all the state a chain needs.
+ *
+ * Accumulator convention: acc = (symbols << 8) | position, position relative to
+ * the current word (< 32 when a word is entered); table entries add
+ * (nsym << 8 | bits) with one instruction (hb_format.h).                      */
 
-/* Walk the chain that starts at entry offset e.  Fills V, returns the position
- * of the first codeword start at or after lim (>= S when lim == S). */
-template <int WPT>
-HB_HD uint32_t hb_walk(const hb_lutref &lut, const uint32_t (&w)[WPT + 1],
-                       uint32_t lim, uint32_t e, uint32_t (&V)[WPT]) {
-    uint32_t pos = e;
-#pragma unroll
-    for (int j = 0; j < WPT; j++) {
-        uint32_t limj = lim < 32u * (j + 1) ? lim : 32u * (j + 1);
-        uint32_t v = 0;
-        while (pos < limj) {
-            uint32_t sym;
-            v |= hb_bit(pos);
-            pos += hb_probe(lut, w[j], w[j + 1], pos, &sym);
-        }
-        V[j] = v;
-    }
-    return pos;
+struct hb_tables {
+    const uint32_t *fast;  /* S- or E-table, 1 << wf entries (host emulation) */
+    uint32_t fast_saddr;   /* its shared-state-space address (device) */
+    uint32_t fmask4;       /* ((1 << wf) - 1) << 2: byte-offset mask */
+    hb_lutref slow;        /* single-symbol multi-level table: long codes, partial words */
+};
+
+HB_HD uint32_t hb_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+#endif
 }
 
-/* Re-walk from a new entry offset e until the chain hits a position already in
- * V (from there on both chains are identical) or runs past lim.  V becomes the
- * chain of e.  Returns true when it merged (the end position is unchanged);
- * otherwise *endpos receives the new end position. */
+HB_HD uint32_t hb_ctz(uint32_t v) {   /* v != 0 */
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)v) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+}
+
+HB_HD uint32_t hb_acc_add(uint32_t acc, uint32_t ent) {   /* acc += ent >> 16 */
+#if defined(__CUDA_ARCH__) && defined(HB_USE_DP2A)
+    return __dp2a_lo(ent, 0x0100u, acc);
+#else
+    return acc + (ent >> 16);
+#endif
+}
+
+HB_HD uint32_t hb_fast_load(const hb_tables &tb, uint32_t lo2, uint32_t hi2, uint32_t acc) {
+    uint32_t x = hb_funnel_r(lo2, hi2, acc) & tb.fmask4;
+#ifdef __CUDA_ARCH__
+    /* explicit shared-space load: a generic pointer makes the compiler rebuild the
+     * shared window base (S2R SR_CgaCtaId ...) on every probe */
+    uint32_t ent;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(x + tb.fast_saddr));
+    return ent;
+#else
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+#endif
+}
+
+/* Full word (bound = 32), multi-symbol S-table probes.  acc: in = chain state on
+ * entering this word, out = state on entering the next word. */
+HB_HD void hb_word_fast(const hb_tables &tb, uint32_t lo, uint32_t hi, uint32_t &acc,
+                        uint32_t &land, uint32_t &cnt) {
+    const uint32_t lo2 = lo << 2, hi2 = hb_funnel_l(lo, hi, 2);   /* window pre-scaled to byte offsets */
+    uint32_t ent, prev;
+    for (;;) {
+        do {
+            ent = hb_fast_load(tb, lo2, hi2, acc);
+            acc = hb_acc_add(acc, ent);
+        } while (!(acc & 0xE0u));
+        prev = acc - (ent >> 16);       /* state before the last probe */
+        if ((acc & 0xffu) < HB_FAST_MARK) break;
+        /* a codeword longer than the table index starts at prev's position */
+        uint32_t sym;
+        uint32_t len = hb_probe(tb.slow, lo, hi, prev & 0xffu, &sym);
+        acc = prev + len + 0x100u;
+        ent = 1u;                       /* one start, at offset 0 of the probe */
+        if (acc & 0xE0u) break;
+    }
+    const uint32_t pb = prev & 0xffu;                 /* position of the last probe (< 32) */
+    const uint32_t spill = hb_funnel_l(ent & 0xffffu, 0u, pb);   /* its starts at or past bit 32 */
+    const uint32_t nsp = (uint32_t)hb_popc(spill);
+    const uint32_t pos = (acc & 0xffu) - 32u;
+    land = spill ? hb_ctz(spill) : pos;
+    cnt = (acc >> 8) - nsp;
+    acc = (nsp << 8) | pos;
+}
+
+/* Any bound (0..32), one symbol per probe: stream tail and cross-checks. */
+HB_HD void hb_word_slow(const hb_lutref &lut, uint32_t lo, uint32_t hi, uint32_t bound,
+                        uint32_t &acc, uint32_t &land, uint32_t &cnt) {
+    uint32_t pos = acc & 0xffu, n = bound ? acc >> 8 : 0u;   /* carried-in starts lie below the entry position */
+    while (pos < bound) {
+        uint32_t sym;
+        pos += hb_probe(lut, lo, hi, pos, &sym);
+        n++;
+    }
+    land = (pos - bound) & 31u;
+    cnt = n;
+    acc = pos >= 32u ? pos - 32u : 0u;   /* after a partial word nothing further is owned */
+}
+
+HB_HD uint32_t hb_rec_pack(uint32_t land, uint32_t cnt) { return land | (cnt << 5); }
+HB_HD uint32_t hb_rec_land(uint32_t r) { return r & 31u; }
+HB_HD uint32_t hb_rec_cnt(uint32_t r) { return r >> 5; }
+
+/* bound of word j of a subsequence whose first lim positions are owned */
+HB_HD uint32_t hb_bound(uint32_t lim, uint32_t j) {
+    return lim >= 32u * (j + 1u) ? 32u : (lim > 32u * j ? lim - 32u * j : 0u);
+}
+
+/* Chain of entry offset e through a whole subsequence (WPT words, w[WPT] = first
+ * word of the next one): fills rec[j] = (land, cnt) per word. */
 template <int WPT>
-HB_HD bool hb_rewalk(const hb_lutref &lut, const uint32_t (&w)[WPT + 1],
-                     uint32_t lim, uint32_t e, uint32_t (&V)[WPT],
-                     uint32_t *endpos) {
-    uint32_t pos = e;
+HB_HD void hb_walk(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t lim, uint32_t e,
+                   uint32_t (&rec)[WPT]) {
+    uint32_t acc = e;
+    if (lim == 32u * WPT) {
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            uint32_t land, cnt;
+            hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
+            rec[j] = hb_rec_pack(land, cnt);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            uint32_t land, cnt;
+            hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, j), acc, land, cnt);
+            rec[j] = hb_rec_pack(land, cnt);
+        }
+    }
+}
+
+/* Re-walk from a new entry offset e, word by word, until the chain lands where
+ * the recorded chain landed (identical from there on) or the subsequence ends.
+ * rec becomes the chain of e.  Returns true when the landing behind the LAST
+ * word changed (the right neighbour's entry offset moves). */
+template <int WPT>
+HB_HD bool hb_rewalk(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t lim, uint32_t e,
+                     uint32_t (&rec)[WPT]) {
+    uint32_t acc = e;
     bool merged = false;
+    const bool full = lim == 32u * WPT;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
         if (!merged) {
-            uint32_t limj = lim < 32u * (j + 1) ? lim : 32u * (j + 1);
-            uint32_t v = 0;
-            while (pos < limj) {
-                uint32_t b = hb_bit(pos);
-                if (V[j] & b) {           /* old chain passes through pos */
-                    v |= V[j] & ~(b - 1u); /* keep its starts at and after pos */
-                    merged = true;
-                    break;
-                }
-                uint32_t sym;
-                v |= b;
-                pos += hb_probe(lut, w[j], w[j + 1], pos, &sym);
-            }
-            V[j] = v;
+            uint32_t land, cnt;
+            if (full) hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
+            else hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, j), acc, land, cnt);
+            merged = land == hb_rec_land(rec[j]);
+            rec[j] = hb_rec_pack(land, cnt);
         }
     }
-    if (!merged) *endpos = pos;
-    return merged;
+    return !merged;
 }
 
-/* Walk the chain of entry e and hand every symbol to sink(n, sym), n = 0,1,...
- * Returns the number of symbols (codewords that start before lim). */
-template <int WPT, class Sink>
-HB_HD uint32_t hb_walk_emit(const hb_lutref &lut, const uint32_t (&w)[WPT + 1],
-                            uint32_t lim, uint32_t e, Sink &sink) {
+/* ==== emit walks: decode the chain of entry e and store its symbols ==========
+ * E-table probes carry up to two symbols.  The second symbol of the last probe
+ * of the LAST word may start in the next subsequence; it is stored only while
+ * its index is below c, the chain's symbol count known from the sync kernel. */
+template <int WPT>
+HB_HD uint32_t hb_emit_fast(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
+                            uint32_t c, uint8_t *out) {
+    uint32_t acc = e;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        const uint32_t lo = w[j], hi = w[j + 1];
+        const uint32_t lo2 = lo << 2, hi2 = hb_funnel_l(lo, hi, 2);
+        uint32_t ent, prev;
+        for (;;) {
+            do {
+                ent = hb_fast_load(tb, lo2, hi2, acc);
+                const uint32_t n = acc >> 8;
+                out[n] = (uint8_t)ent;
+                if (j < WPT - 1) { if (ent & (2u << 24)) out[n + 1] = (uint8_t)(ent >> 8); }
+                else { if ((ent & (2u << 24)) && n + 1 < c) out[n + 1] = (uint8_t)(ent >> 8); }
+                acc = hb_acc_add(acc, ent);
+            } while (!(acc & 0xE0u));
+            prev = acc - (ent >> 16);
+            if ((acc & 0xffu) < HB_FAST_MARK) break;
+            uint32_t sym;
+            uint32_t len = hb_probe(tb.slow, lo, hi, prev & 0xffu, &sym);
+            out[prev >> 8] = (uint8_t)sym;
+            acc = prev + len + 0x100u;
+            if (acc & 0xE0u) break;
+        }
+        acc -= 32u;
+    }
+    return acc >> 8 < c ? acc >> 8 : c;
+}
+
+template <int WPT>
+HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], uint32_t lim,
+                            uint32_t e, uint32_t c, uint8_t *out) {
     uint32_t pos = e, n = 0;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
-        uint32_t limj = lim < 32u * (j + 1) ? lim : 32u * (j + 1);
+        const uint32_t limj = lim < 32u * (j + 1) ? lim : 32u * (j + 1);
         while (pos < limj) {
             uint32_t sym;
             pos += hb_probe(lut, w[j], w[j + 1], pos, &sym);
-            sink(n, sym);
+            if (n < c) out[n] = (uint8_t)sym;
             n++;
         }
     }
-    return n;
+    return n < c ? n : c;
 }
 
 /* ==== tile-level walks over shared-memory copies ===========================
  * comp: the tile's T*WPT words followed by the first word of the next tile.
- * Vs:   converged chain of the "entry offset 0" hypothesis, Vs[j*T + t].
- * cs:   exclusive prefix of the per-subsequence symbol counts of that chain.
- * tile_lim: number of leading bit positions of the tile at which a codeword
- *       may start (T*S except in the last tile); avail: number of stream bits
- *       from the start of the tile to the end of the data (a codeword that
- *       would end after avail is incomplete and is not counted, as in the
- *       reference's serial decoder which only emits on reaching a leaf).     */
+ * recs: converged records of the "tile entry offset 0" chain, recs[j*T + t].
+ * cs:   exclusive prefix over subsequences of that chain's symbol counts.
+ * tile_lim: number of leading bit positions of the tile that are owned.       */
 
-/* Chain of a non-zero tile entry offset e: follow it until it joins the
- * hypothesis-0 chain (then exit and tail count are those of hypothesis 0) or
- * leaves the tile.  Outputs packed (count << 8) | exit. */
+/* Chain of a non-zero tile entry offset e: follow it word by word until it lands
+ * where the hypothesis-0 chain landed (exit and remaining count are then those
+ * of hypothesis 0) or leaves the tile.  Returns packed (count << 8) | exit. */
 template <int WPT, int T>
-HB_HD uint32_t hb_hyp_walk(const hb_lutref &lut, const uint32_t *comp,
-                           const uint32_t *Vs, const uint32_t *cs,
-                           uint32_t C0, uint32_t X0, uint32_t tile_lim,
-                           uint32_t avail, uint32_t e) {
-    constexpr uint32_t S = 32u * WPT;
-    uint32_t q = e, n = 0;
-    for (;;) {
-        if (q >= tile_lim) return hb_map_pack32((q - tile_lim) & 31u, n);
-        uint32_t t = q / S, j = (q >> 5) & (WPT - 1u);
-        uint32_t vw = Vs[j * T + t], b = hb_bit(q);
-        if (vw & b) {
-            uint32_t below = cs[t] + hb_popc(vw & (b - 1u));
-            for (uint32_t jj = 0; jj < j; jj++) below += hb_popc(Vs[jj * T + t]);
-            return hb_map_pack32(X0 & 31u, n + C0 - below);
+HB_HD uint32_t hb_hyp_walk(const hb_tables &tb, const uint32_t *comp, const uint32_t *recs,
+                           const uint32_t *cs, uint32_t C0, uint32_t X0, uint32_t tile_lim,
+                           uint32_t e) {
+    uint32_t acc = e, n = 0, land = e;
+    const uint32_t nwords = (tile_lim + 31u) >> 5;
+    for (uint32_t wi = 0; wi < nwords; wi++) {
+        const uint32_t left = tile_lim - 32u * wi;
+        const uint32_t bound = left >= 32u ? 32u : left;
+        uint32_t cnt;
+        /* multi-symbol probes may carry starts into the next word; that is only
+         * exact when the next word is fully owned or not owned at all */
+        if (left >= 64u || left == 32u) hb_word_fast(tb, comp[wi], comp[wi + 1], acc, land, cnt);
+        else hb_word_slow(tb.slow, comp[wi], comp[wi + 1], bound, acc, land, cnt);
+        n += cnt;
+        const uint32_t t = wi / WPT, j = wi % WPT;
+        if (land == hb_rec_land(recs[j * T + t])) {
+            uint32_t upto = cs[t];                    /* hypothesis-0 symbols through word wi */
+            for (uint32_t jj = 0; jj <= j; jj++) upto += hb_rec_cnt(recs[jj * T + t]);
+            return hb_map_pack32(X0 & 31u, n + C0 - upto);
         }
-        uint32_t sym;
-        uint32_t len = hb_probe(lut, comp[q >> 5], comp[(q >> 5) + 1], q, &sym);
-        if (q + len > avail) return hb_map_pack32(0, n);
-        q += len;
-        n++;
     }
+    return hb_map_pack32(land & 31u, n);
 }
 
-/* The true entry offset E of a tile differs from the stored hypothesis: redo
- * the (entry, count) records of the leading subsequences until the chain of E
- * enters a subsequence at the offset already on record. */
-template <int WPT, int T>
-HB_HD void hb_fix_entries(const hb_lutref &lut, const uint32_t *comp,
-                          uint16_t *sub, uint32_t tile_lim, uint32_t avail,
-                          uint32_t E) {
+/* The true entry offset E of a tile differs from the recorded hypothesis (0):
+ * redo the (entry, count) records of the leading subsequences until the chain
+ * of E enters a subsequence at the offset already on record.  word(i) returns
+ * stream word i of the tile (0 past the end of the data); sub points at the
+ * tile's T records. */
+template <int WPT, int T, class WordFn>
+HB_HD void hb_fix_entries(const hb_tables &tb, const WordFn &word, uint16_t *sub,
+                          uint32_t tile_lim, uint32_t E) {
     constexpr uint32_t S = 32u * WPT;
     uint32_t e = E;
     for (uint32_t t = 0; t < (uint32_t)T; t++) {
-        uint32_t s0 = t * S;
+        const uint32_t s0 = t * S;
         if (s0 >= tile_lim) break;
         if (hb_sub_entry(sub[t]) == e) break;
-        uint32_t lim = tile_lim - s0 < S ? tile_lim - s0 : S;
-        uint32_t pos = e, n = 0;
-        while (pos < lim) {
-            uint32_t q = s0 + pos, sym;
-            uint32_t len = hb_probe(lut, comp[q >> 5], comp[(q >> 5) + 1], q, &sym);
-            if (q + len > avail) { pos = S + 31u; break; }
-            pos += len;
-            n++;
+        const uint32_t lim = tile_lim - s0 < S ? tile_lim - s0 : S;
+        uint32_t acc = e, n = 0, land = e;
+        uint32_t lo = word(t * WPT);
+        for (uint32_t j = 0; j < (uint32_t)WPT; j++) {
+            const uint32_t hi = word(t * WPT + j + 1);
+            uint32_t cnt;
+            if (lim == S) hb_word_fast(tb, lo, hi, acc, land, cnt);
+            else hb_word_slow(tb.slow, lo, hi, hb_bound(lim, j), acc, land, cnt);
+            n += cnt;
+            lo = hi;
         }
         sub[t] = hb_sub_pack(e, n);
-        e = (pos - S) & 31u;
+        e = land;
     }
 }
 

@@ -2,5 +2,22 @@
 #ifndef HB_FORMAT_H_
 #define HB_FORMAT_H_
 #define HB_MAX_CODELEN 32          /* longest supported codeword (bits) */
-#define HB_LUT_LINK 0x80000000u    /* LUT entry flag: continue in a sub-table */
+#define HB_LUT_LINK 0x80000000u    /* single-symbol LUT entry flag: continue in a sub-table */
+
+/* Multi-symbol ("fast") tables, indexed by the next wf stream bits (LSB first).
+ * From offset 0 of the index, consecutive codewords are decoded while they lie
+ * entirely inside the wf bits.  Both tables pack, in their high half,
+ *     [23:16] B    = bits consumed by those codewords
+ *     [31:24] nsym = how many there are
+ * so that `acc += entry >> 16` advances a packed (symbols << 8 | bit position)
+ * accumulator in one add.  Low half:
+ *   S-table (sync kernel): [15:0] bitmask of the codeword START offsets
+ *   E-table (emit kernel): [7:0] first symbol, [15:8] second symbol (at most
+ *                          HB_E_MAXSYM symbols per entry)
+ * When not even the first codeword fits (code longer than wf bits) the entry is
+ * the marker: nsym = 0, B = HB_FAST_MARK, low half 0; adding it pushes the
+ * position byte past any legal value, which ends the probe loop. */
+#define HB_FAST_MARK 0xE0u
+#define HB_E_MAXSYM 2
+#define HB_WF_MAX 12               /* widest fast-table index (16 KB per table) */
 #endif

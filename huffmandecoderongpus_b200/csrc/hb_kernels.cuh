@@ -36,14 +36,16 @@ struct hb_stream_args {
     uint64_t bits_own;       /* codewords starting before this bit are ours */
     uint64_t bits_avail;     /* valid bits in words[] (>= bits_own) */
     uint32_t ntiles;
-    const uint32_t *lut;     /* whole LUT in global memory */
-    uint32_t w1;             /* level-1 width */
+    const uint32_t *lut;     /* single-symbol multi-level LUT in global memory */
+    uint32_t w1;             /* its level-1 width */
     uint32_t maxlen;         /* number of candidate entry offsets to resolve */
+    const uint32_t *fast;    /* S-table (sync kernel) or E-table (emit kernel), 1 << wf entries */
+    uint32_t wf;
 };
 
-/* level-1 table footprint in shared memory, kept a multiple of 16 bytes */
-__host__ __device__ __forceinline__ uint32_t hb_lut_smem_words(uint32_t w1) {
-    return ((1u << w1) + 3u) & ~3u;
+/* fast-table footprint in shared memory, kept a multiple of 16 bytes */
+__host__ __device__ __forceinline__ uint32_t hb_lut_smem_words(uint32_t wf) {
+    return ((1u << wf) + 3u) & ~3u;
 }
 
 /* device status word bits */
@@ -104,18 +106,22 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* S-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_lut = smem;
-    uint32_t *s_comp = s_lut + hb_lut_smem_words(a.w1);   /* T*WPT + 4 */
-    uint32_t *s_V = s_comp + T * WPT + 4;         /* WPT*T */
-    uint32_t *s_cs = s_V + WPT * T;               /* T */
-    uint32_t *s_end = s_cs + T;                   /* T */
-    uint32_t *s_warp = s_end + T;                 /* 16 */
+    uint32_t *s_comp = smem;                               /* T*WPT + 4 */
+    uint32_t *s_rec = s_comp + T * WPT + 4;                /* WPT*T per-word (land, cnt) */
+    uint32_t *s_cs = s_rec + WPT * T;                      /* T */
+    uint32_t *s_land = s_cs + T;                           /* T: landing behind each subsequence */
+    uint32_t *s_warp = s_land + T;                         /* 16 */
     const int t = threadIdx.x;
 
-    for (uint32_t i = t; i < (1u << a.w1); i += T) s_lut[i] = __ldg(a.lut + i);
+    for (uint32_t i = t; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
     __syncthreads();
-    hb_lutref lut{s_lut, a.lut, (1u << a.w1) - 1u};
+    hb_tables tb;
+    tb.fast = s_fast;
+    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
 
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
@@ -130,41 +136,35 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
 
         /* chain of the guess "a codeword starts at offset 0 of my subsequence" */
-        uint32_t V[WPT];
+        uint32_t rec[WPT];
         uint32_t e = 0;
-        uint32_t endpos = hb_walk<WPT>(lut, w, lim, 0u, V);
-        s_end[t] = endpos;
+        hb_walk<WPT>(tb, w, lim, 0u, rec);
+        s_land[t] = hb_rec_land(rec[WPT - 1]);
         __syncthreads();
 
-        /* stitch: my true entry is where my left neighbour's chain ends; repeat
-         * until nobody's end position moves (1-3 rounds on self-synchronising
-         * data, at most T rounds in general) */
+        /* stitch: my true entry is where my left neighbour's chain lands; repeat
+         * until no landing moves (1-3 rounds on self-synchronising data, at most
+         * T rounds in general) */
         for (;;) {
             bool changed = false;
             if (t > 0 && lim > 0) {
-                uint32_t en = (s_end[t - 1] - S) & 31u;
+                const uint32_t en = s_land[t - 1];
                 if (en != e) {
                     e = en;
-                    uint32_t np;
-                    if (!hb_rewalk<WPT>(lut, w, lim, e, V, &np) && np != endpos) {
-                        endpos = np;
-                        changed = true;
-                    }
+                    changed = hb_rewalk<WPT>(tb, w, lim, e, rec);
                 }
             }
             if (!__syncthreads_or(changed)) break;
-            s_end[t] = endpos;
+            s_land[t] = hb_rec_land(rec[WPT - 1]);
             __syncthreads();
         }
 
         uint32_t c = 0;
 #pragma unroll
         for (int j = 0; j < WPT; j++) {
-            c += __popc(V[j]);
-            s_V[j * T + t] = V[j];
+            c += hb_rec_cnt(rec[j]);
+            s_rec[j * T + t] = rec[j];
         }
-        /* a last codeword that runs past the end of the data is not a symbol */
-        if (c && sub0 + endpos > a.bits_avail) c--;
         subs[(uint64_t)tile * T + t] = hb_sub_pack(e, c);
 
         uint32_t C0;
@@ -173,18 +173,15 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
         __syncthreads();
 
         /* tile map: hypothesis 0 is the converged chain; hypotheses 1..maxlen-1
-         * are followed by one lane each until they join it */
+         * are followed by one lane each until they land on it */
         if (t < 32) {
             const uint64_t own_left = a.bits_own - tile_bit0;   /* tile < ntiles => > 0 */
-            const uint64_t av_left = a.bits_avail - tile_bit0;
             const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
-            const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
-            /* exit of hypothesis 0: end of the last active subsequence's chain */
-            const uint32_t tl = (tile_lim - 1u) / S;
-            const uint32_t X0 = (tl * S + s_end[tl] - tile_lim) & 31u;
+            const uint32_t wl = (tile_lim - 1u) >> 5;           /* last owned word */
+            const uint32_t X0 = hb_rec_land(s_rec[(wl % WPT) * T + wl / WPT]);
             uint32_t m = hb_map_pack32(X0, C0);
             if (t > 0 && (uint32_t)t < a.maxlen)
-                m = hb_hyp_walk<WPT, T>(lut, s_comp, s_V, s_cs, C0, X0, tile_lim, avail, (uint32_t)t);
+                m = hb_hyp_walk<WPT, T>(tb, s_comp, s_rec, s_cs, C0, X0, tile_lim, (uint32_t)t);
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
         __syncthreads();
@@ -281,14 +278,15 @@ __global__ void hb_compose_kernel(const uint64_t *__restrict__ all_maps, int n_r
 }
 
 /* down-sweep: fix the entry offset and output base of every tile.
- * result[0] = symbols of this shard, [1] = exit offset, [2] = entry, [3] = base */
+ * result[0] = symbols of this shard, [1] = exit offset, [2] = entry, [3] = base.
+ * One CTA more than needed is harmless; launched after hb_scan_top_kernel. */
 __global__ void __launch_bounds__(HB_SCAN_T)
 hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
                     const uint64_t *__restrict__ wmaps, const uint64_t *__restrict__ cprefix,
                     const uint64_t *__restrict__ shard_map,
                     const uint64_t *__restrict__ entry_base,
                     uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
-                    uint64_t *__restrict__ result) {
+                    uint64_t *__restrict__ result, uint64_t bits_own, uint64_t bits_avail) {
     __shared__ uint32_t s_we[32];
     __shared__ uint64_t s_wb[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -297,7 +295,11 @@ hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
     const uint64_t cp = __ldg(cprefix + (uint64_t)blockIdx.x * 32 + E);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t sm = shard_map[E];
-        result[0] = sm >> 8;
+        uint64_t total = sm >> 8;
+        /* the serial decoder emits a symbol only on reaching a leaf: a last
+         * codeword that runs past the end of the data is not a symbol */
+        if (total && bits_own + (sm & 31u) > bits_avail) total--;
+        result[0] = total;
         result[1] = sm & 31u;
         result[2] = E;
         result[3] = B;
@@ -348,59 +350,73 @@ hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
 }
 
 /* ------------------------------------------------------------------------- */
-struct hb_stage_sink {
-    uint8_t *p;
-    __device__ __forceinline__ void operator()(uint32_t n, uint32_t sym) const {
-        p[n] = (uint8_t)sym;
+/* One thread per tile: where the tile's true entry offset differs from the
+ * hypothesis the sync kernel recorded (0), re-chain the leading subsequences
+ * (typically 1-2) and rewrite their (entry, count) records in place.  All tiles
+ * in parallel; uses the S-table, so the emit kernel needs only the E-table. */
+struct hb_tile_words {
+    const uint32_t *words;
+    uint64_t base, nwords;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return base + i < nwords ? __ldg(words + base + i) : 0u;
     }
 };
 
 template <int WPT>
 __global__ void __launch_bounds__(HB_T)
+hb_fix_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry, uint16_t *__restrict__ subs) {
+    constexpr int T = HB_T;
+    constexpr uint32_t TS = T * 32u * WPT;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];
+    for (uint32_t i = threadIdx.x; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
+    __syncthreads();
+    hb_tables tb;
+    tb.fast = s_fast;
+    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    const uint32_t tile = blockIdx.x * T + threadIdx.x;
+    if (tile >= a.ntiles) return;
+    const uint32_t E = tile_entry[tile];
+    if (E == 0) return;
+    const uint64_t own_left = a.bits_own - (uint64_t)tile * TS;
+    const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+    hb_tile_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
+    hb_fix_entries<WPT, T>(tb, word, subs + (uint64_t)tile * T, tile_lim, E);
+}
+
+/* ------------------------------------------------------------------------- */
+template <int WPT>
+__global__ void __launch_bounds__(HB_T)
 hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
-               const uint8_t *__restrict__ tile_entry, const uint64_t *__restrict__ tile_base,
-               uint8_t *__restrict__ out, uint64_t out_capacity, uint32_t stage_bytes,
-               uint32_t *__restrict__ status) {
+               const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
+               uint64_t out_capacity, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* E-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_lut = smem;
-    uint32_t *s_comp = s_lut + hb_lut_smem_words(a.w1);  /* T*WPT + 4 */
-    uint32_t *s_warp = s_comp + T * WPT + 4;          /* 16 */
-    uint16_t *s_sub = reinterpret_cast<uint16_t *>(s_warp + 16);   /* T u16 = T/2 words */
-    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16 + T / 2);  /* stage_bytes, 16-aligned */
+    uint32_t *s_warp = smem;                               /* 16 */
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
     const int t = threadIdx.x;
 
-    for (uint32_t i = t; i < (1u << a.w1); i += T) s_lut[i] = __ldg(a.lut + i);
+    for (uint32_t i = t; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
     __syncthreads();
-    hb_lutref lut{s_lut, a.lut, (1u << a.w1) - 1u};
+    hb_tables tb;
+    tb.fast = s_fast;
+    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    const uint64_t total_valid = result[0];
 
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
-        const uint32_t E = tile_entry[tile];
         const uint64_t B = tile_base[tile];
         uint32_t w[WPT + 1];
         hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-        uint16_t sub = subs[(uint64_t)tile * T + t];
+        const uint16_t sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
 
-        if (E != 0) {   /* block-uniform: the stored records assume entry offset 0 */
-#pragma unroll
-            for (int j = 0; j < WPT; j++) s_comp[t * WPT + j] = w[j];
-            if (t == T - 1) s_comp[T * WPT] = w[WPT];
-            s_sub[t] = sub;
-            __syncthreads();
-            if (t == 0) {
-                const uint64_t own_left = a.bits_own - tile_bit0;
-                const uint64_t av_left = a.bits_avail - tile_bit0;
-                const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
-                const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
-                hb_fix_entries<WPT, T>(lut, s_comp, s_sub, tile_lim, avail, E);
-            }
-            __syncthreads();
-            sub = s_sub[t];
-        }
         const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
         uint32_t nk;
         const uint32_t o = hb_block_exscan(c, s_warp, &nk);
@@ -408,12 +424,16 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
         const uint32_t lim = sub0 >= a.bits_own ? 0u
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
         const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B) & 15u);
-        hb_stage_sink sink{s_out + al + o};
-        if (c) hb_walk_emit<WPT>(lut, w, lim, e, sink);
+        if (c) {
+            if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, s_out + al + o);
+            else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, s_out + al + o);
+        }
         __syncthreads();
 
         /* staging -> global: s_out[al + i] -> out[B + i], 16-byte vectors aligned
          * in both spaces, partial first/last vectors byte-wise */
+        if (B < total_valid && B + nk > total_valid) nk = (uint32_t)(total_valid - B);
+        else if (B >= total_valid) nk = 0;
         if (B + nk > out_capacity) {
             if (t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
         } else {
@@ -433,7 +453,6 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             }
         }
         __syncthreads();
-        (void)stage_bytes;
     }
 }
 

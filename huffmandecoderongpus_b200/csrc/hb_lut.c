@@ -30,6 +30,7 @@ typedef struct builder {
 } builder;
 
 static int is_leaf(const hb_node *n) { return n->izero == -1 && n->ione == -1; }
+static int build_fast_tables(const hb_node *tree, hb_lut *out);
 
 /* iterative validation: every reachable node is a full internal node or a leaf,
  * indices in range, no node reached twice (=> a tree, no cycles), depth <= 32 */
@@ -182,12 +183,64 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
     uint8_t have[256];
     memset(have, 0, sizeof(have));
     collect_codes(tree, 0, 0, 0, out, have);
+    int frc = build_fast_tables(tree, out);
+    if (frc != HB_OK) { hb_lut_free(out); return frc; }
+    return HB_OK;
+}
+
+/* ---- multi-symbol tables -----------------------------------------------------
+ * The reference has a CPU precedent for several symbols per table entry
+ * (decodeBigtableMultiSym, framework/mainrun.c:209-247,300-352: up to 6 symbols
+ * per 2^height-entry cell); here the index is only wf <= 12 bits wide so that a
+ * table fits shared memory, and the sync kernel's variant carries the start
+ * offsets instead of the symbols. */
+static int build_fast_tables(const hb_node *tree, hb_lut *out) {
+    uint32_t wf = out->maxlen < HB_WF_MAX ? out->maxlen : HB_WF_MAX;
+    uint32_t n = 1u << wf;
+    out->wf = wf;
+    out->stab = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    out->etab = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    if (!out->stab || !out->etab) return HB_ERR_NOMEM;
+    for (uint32_t x = 0; x < n; x++) {
+        uint32_t sm = 0, nsym = 0, used = 0;       /* unlimited symbols (S-table) */
+        uint32_t e_syms = 0, e_nsym = 0, e_used = 0; /* at most HB_E_MAXSYM (E-table) */
+        uint32_t pos = 0;
+        for (;;) {
+            int32_t node = 0;
+            uint32_t p = pos;
+            while (!is_leaf(&tree[node]) && p < wf) {
+                node = ((x >> p) & 1u) ? tree[node].ione : tree[node].izero;
+                p++;
+            }
+            if (!is_leaf(&tree[node])) break;      /* next codeword does not fit */
+            sm |= 1u << pos;
+            nsym++;
+            used = p;
+            if (e_nsym < HB_E_MAXSYM) {
+                e_syms |= (uint32_t)tree[node].sym << (8 * e_nsym);
+                e_nsym++;
+                e_used = p;
+            }
+            pos = p;
+            if (pos >= wf) break;
+        }
+        if (nsym == 0) {
+            out->stab[x] = HB_FAST_MARK << 16;
+            out->etab[x] = HB_FAST_MARK << 16;
+        } else {
+            out->stab[x] = sm | (used << 16) | (nsym << 24);
+            out->etab[x] = e_syms | (e_used << 16) | (e_nsym << 24);
+        }
+    }
     return HB_OK;
 }
 
 void hb_lut_free(hb_lut *lut) {
     if (!lut) return;
     free(lut->entries);
+    free(lut->stab);
+    free(lut->etab);
     lut->entries = NULL;
+    lut->stab = lut->etab = NULL;
     lut->n_entries = 0;
 }

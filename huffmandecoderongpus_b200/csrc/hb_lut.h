@@ -23,6 +23,10 @@ typedef struct hb_lut {
     uint32_t  maxlen;    /* longest codeword (reference tableHeight)   */
     uint32_t  minlen;    /* shortest codeword (reference tableMinDepth) */
     uint32_t  n_leaves;
+    /* multi-symbol tables (hb_format.h), 1 << wf entries each */
+    uint32_t  wf;
+    uint32_t *stab;
+    uint32_t *etab;
     /* canonical per-symbol code (first leaf found for each symbol), used by the
      * bundled encoder: code bits LSB-first in stream order */
     uint32_t  code[256];

@@ -37,26 +37,13 @@ struct emul_stats {
     uint64_t long_probes;       /* probes that needed a second-level table */
 };
 
-static thread_local uint64_t g_probe_count;
-
-/* counting wrappers: the probe itself is hb_probe from hb_core.cuh */
-template <int WPT>
-static uint32_t walk_counted(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], uint32_t lim,
-                             uint32_t e, uint32_t (&V)[WPT], uint64_t *n) {
-    uint32_t end = hb_walk<WPT>(lut, w, lim, e, V);
-    uint64_t c = 0;
-    for (int j = 0; j < WPT; j++) c += hb_popc(V[j]);
-    *n = c;
-    return end;
-}
-
 template <int WPT, int T>
 struct Emul {
     static constexpr uint32_t S = 32u * WPT;
     static constexpr uint32_t TS = T * S;
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
-    hb_lutref lut; uint32_t maxlen;
+    hb_tables tbS, tbE; uint32_t maxlen;
     std::vector<uint16_t> subs;
     std::vector<uint32_t> tmaps;
     std::vector<uint64_t> wmaps, cmaps, cprefix;
@@ -68,111 +55,99 @@ struct Emul {
     void load(uint64_t wbase, uint32_t (&w)[WPT + 1]) {
         for (int j = 0; j <= WPT; j++) w[j] = (wbase + j < nwords) ? words[wbase + j] : 0u;
     }
+    static uint32_t total(const uint32_t (&rec)[WPT]) {
+        uint32_t c = 0;
+        for (int j = 0; j < WPT; j++) c += hb_rec_cnt(rec[j]);
+        return c;
+    }
 
     /* mirrors hb_sync_kernel, one tile */
     void sync_tile(uint32_t tile) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
-        std::vector<uint32_t> s_comp(T * WPT + 4, 0), s_V(WPT * T, 0), s_cs(T, 0), s_end(T, 0);
-        std::vector<uint32_t> lim(T), e(T, 0), endpos(T), c(T);
+        std::vector<uint32_t> s_comp(T * WPT + 4, 0), s_rec(WPT * T, 0), s_cs(T, 0), s_land(T, 0);
+        std::vector<uint32_t> lim(T), e(T, 0);
         std::vector<std::array<uint32_t, WPT + 1>> W(T);
-        std::vector<std::array<uint32_t, WPT>> V(T);
+        std::vector<std::array<uint32_t, WPT>> R(T);
         std::vector<uint32_t> trips(T, 0);
         for (int t = 0; t < T; t++) {
-            uint32_t w[WPT + 1];
+            uint32_t w[WPT + 1], rec[WPT];
             load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
             for (int j = 0; j <= WPT; j++) W[t][j] = w[j];
             for (int j = 0; j < WPT; j++) s_comp[t * WPT + j] = w[j];
             if (t == T - 1) s_comp[T * WPT] = w[WPT];
             const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
             lim[t] = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
-            uint32_t v[WPT];
-            uint64_t n;
-            endpos[t] = walk_counted<WPT>(lut, w, lim[t], 0u, v, &n);
-            for (int j = 0; j < WPT; j++) V[t][j] = v[j];
-            st.probes_walk += n;
-            trips[t] = (uint32_t)n;
-            s_end[t] = endpos[t];
+            hb_walk<WPT>(tbS, w, lim[t], 0u, rec);
+            /* cross-check: the multi-symbol walk equals the symbol-by-symbol walk */
+            if (lim[t] == S) {
+                uint32_t acc = 0;
+                for (int j = 0; j < WPT; j++) {
+                    uint32_t land, cnt;
+                    hb_word_slow(tbS.slow, w[j], w[j + 1], 32u, acc, land, cnt);
+                    if (hb_rec_pack(land, cnt) != rec[j]) st.long_probes |= 1ull << 63;  /* flag */
+                }
+            }
+            for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
+            st.probes_walk += total(rec);
+            trips[t] = total(rec);
+            s_land[t] = hb_rec_land(rec[WPT - 1]);
         }
         for (int w0 = 0; w0 < T; w0 += 32)
             st.warp_iters_walk += *std::max_element(trips.begin() + w0, trips.begin() + std::min(T, w0 + 32));
         uint64_t rounds = 0;
         for (;;) {
             bool any = false;
-            std::vector<uint32_t> new_end(endpos);
+            std::vector<uint32_t> new_land(s_land);
             std::fill(trips.begin(), trips.end(), 0);
             for (int t = 0; t < T; t++) {
                 if (t > 0 && lim[t] > 0) {
-                    uint32_t en = (s_end[t - 1] - S) & 31u;
+                    uint32_t en = s_land[t - 1];
                     if (en != e[t]) {
                         e[t] = en;
-                        uint32_t w[WPT + 1], v[WPT], np = 0;
+                        uint32_t w[WPT + 1], rec[WPT], old[WPT];
                         for (int j = 0; j <= WPT; j++) w[j] = W[t][j];
-                        for (int j = 0; j < WPT; j++) v[j] = V[t][j];
-                        uint32_t before = 0;
-                        for (int j = 0; j < WPT; j++) before += hb_popc(v[j]);
-                        /* count probes = new starts added before the merge point */
-                        uint32_t old[WPT];
-                        for (int j = 0; j < WPT; j++) old[j] = v[j];
-                        bool merged = hb_rewalk<WPT>(lut, w, lim[t], en, v, &np);
-                        uint32_t added = 0;
-                        for (int j = 0; j < WPT; j++) added += hb_popc(v[j] & ~old[j]);
-                        st.probes_rewalk += added;
-                        trips[t] = added;
-                        for (int j = 0; j < WPT; j++) V[t][j] = v[j];
-                        if (!merged && np != endpos[t]) { new_end[t] = np; any = true; }
+                        for (int j = 0; j < WPT; j++) old[j] = rec[j] = R[t][j];
+                        bool changed = hb_rewalk<WPT>(tbS, w, lim[t], en, rec);
+                        uint32_t walked = 0;   /* words re-walked, for the cost estimate */
+                        for (int j = 0; j < WPT; j++) {
+                            walked++;
+                            if (hb_rec_land(rec[j]) == hb_rec_land(old[j])) break;
+                        }
+                        for (int j = 0; j < (int)walked && j < WPT; j++) { st.probes_rewalk += hb_rec_cnt(rec[j]); trips[t] += hb_rec_cnt(rec[j]); }
+                        for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
+                        new_land[t] = hb_rec_land(rec[WPT - 1]);
+                        if (changed) any = true;
                     }
                 }
             }
             for (int w0 = 0; w0 < T; w0 += 32)
                 st.warp_iters_rewalk += *std::max_element(trips.begin() + w0, trips.begin() + std::min(T, w0 + 32));
-            endpos = new_end;
             rounds++;
             if (!any) break;
-            for (int t = 0; t < T; t++) s_end[t] = endpos[t];
+            s_land = new_land;
         }
         st.rounds_total += rounds;
         st.rounds_max = std::max<uint64_t>(st.rounds_max, rounds);
         uint32_t C0 = 0;
         for (int t = 0; t < T; t++) {
-            const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
             uint32_t cc = 0;
-            for (int j = 0; j < WPT; j++) { cc += hb_popc(V[t][j]); s_V[j * T + t] = V[t][j]; }
-            if (cc && sub0 + endpos[t] > bits_avail) cc--;
-            c[t] = cc;
+            for (int j = 0; j < WPT; j++) { cc += hb_rec_cnt(R[t][j]); s_rec[j * T + t] = R[t][j]; }
             subs[(uint64_t)tile * T + t] = hb_sub_pack(e[t], cc);
             s_cs[t] = C0;
             C0 += cc;
         }
-        /* note: the kernel re-publishes s_end only inside the loop; after the
-         * final (no-change) round s_end equals endpos */
-        for (int t = 0; t < T; t++) s_end[t] = endpos[t];
-        const uint64_t own_left = bits_own - tile_bit0, av_left = bits_avail - tile_bit0;
+        const uint64_t own_left = bits_own - tile_bit0;
         const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
-        const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
-        const uint32_t tl = (tile_lim - 1u) / S;
-        const uint32_t X0 = (tl * S + s_end[tl] - tile_lim) & 31u;
-        uint32_t maxtrip = 0;
+        const uint32_t wl = (tile_lim - 1u) >> 5;
+        const uint32_t X0 = hb_rec_land(s_rec[(wl % WPT) * T + wl / WPT]);
         for (uint32_t t = 0; t < 32; t++) {
             uint32_t m = hb_map_pack32(X0, C0);
             if (t > 0 && t < maxlen) {
-                m = hb_hyp_walk<WPT, T>(lut, s_comp.data(), s_V.data(), s_cs.data(), C0, X0, tile_lim, avail, t);
-                /* cost accounting: re-run to count steps */
-                uint32_t q = t, steps = 0;
-                bool merged = false;
-                while (q < tile_lim) {
-                    uint32_t tt = q / S, j = (q >> 5) & (WPT - 1u);
-                    if (s_V[j * T + tt] & hb_bit(q)) { merged = true; break; }
-                    uint32_t sym, len = hb_probe(lut, s_comp[q >> 5], s_comp[(q >> 5) + 1], q, &sym);
-                    if (q + len > avail) break;
-                    q += len; steps++;
-                }
-                st.probes_hyp += steps;
-                maxtrip = std::max(maxtrip, steps);
-                if (!merged) st.hyp_unmerged++;
+                m = hb_hyp_walk<WPT, T>(tbS, s_comp.data(), s_rec.data(), s_cs.data(), C0, X0, tile_lim, t);
+                if ((m & 31u) != X0) st.hyp_unmerged++;
             }
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
-        st.warp_iters_hyp += maxtrip;
     }
 
     /* mirrors hb_scan_up_kernel / hb_scan_top_kernel */
@@ -216,7 +191,9 @@ struct Emul {
     void scan_down(uint32_t E, uint64_t B, uint64_t *result) {
         const uint32_t ncta = (ntiles + 1023u) / 1024u;
         tile_entry.assign(ntiles, 0); tile_base.assign(ntiles, 0);
-        result[0] = shard_map[E] >> 8; result[1] = shard_map[E] & 31u; result[2] = E; result[3] = B;
+        uint64_t total = shard_map[E] >> 8;
+        if (total && bits_own + (shard_map[E] & 31u) > bits_avail) total--;
+        result[0] = total; result[1] = shard_map[E] & 31u; result[2] = E; result[3] = B;
         for (uint32_t cta = 0; cta < ncta; cta++) {
             uint64_t cp = cprefix[(uint64_t)cta * 32 + E];
             uint32_t cur = (uint32_t)cp & 31u; uint64_t b = cp >> 8;
@@ -239,58 +216,56 @@ struct Emul {
         }
     }
 
-    struct Sink { uint8_t *p; void operator()(uint32_t n, uint32_t sym) const { p[n] = (uint8_t)sym; } };
+    /* mirrors hb_fix_kernel, one tile */
+    void fix_tile(uint32_t tile) {
+        const uint32_t E = tile_entry[tile];
+        if (E == 0) return;
+        st.tiles_entry_nonzero++;
+        const uint64_t own_left = bits_own - (uint64_t)tile * TS;
+        const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+        const uint64_t base = (uint64_t)tile * (T * WPT);
+        auto word = [&](uint32_t i) -> uint32_t { return base + i < nwords ? words[base + i] : 0u; };
+        std::vector<uint16_t> before(subs.begin() + (size_t)tile * T, subs.begin() + (size_t)(tile + 1) * T);
+        hb_fix_entries<WPT, T>(tbS, word, subs.data() + (size_t)tile * T, tile_lim, E);
+        for (int t = 0; t < T; t++)
+            if (before[t] != subs[(size_t)tile * T + t]) st.probes_fix += hb_sub_count(subs[(size_t)tile * T + t]);
+    }
 
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
-    bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t stage_bytes) {
+    bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t stage_bytes, uint64_t total_valid) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
-        const uint32_t E = tile_entry[tile];
         const uint64_t B = tile_base[tile];
-        std::vector<uint32_t> s_comp(T * WPT + 4, 0);
-        std::vector<uint16_t> s_sub(T);
         std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
-        std::vector<std::array<uint32_t, WPT + 1>> W(T);
-        for (int t = 0; t < T; t++) {
-            uint32_t w[WPT + 1];
-            load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-            for (int j = 0; j <= WPT; j++) W[t][j] = w[j];
-            for (int j = 0; j < WPT; j++) s_comp[t * WPT + j] = w[j];
-            if (t == T - 1) s_comp[T * WPT] = w[WPT];
-            s_sub[t] = subs[(uint64_t)tile * T + t];
-        }
-        if (E != 0) {
-            st.tiles_entry_nonzero++;
-            const uint64_t own_left = bits_own - tile_bit0, av_left = bits_avail - tile_bit0;
-            const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
-            const uint32_t avail = av_left < 0xffffffffull ? (uint32_t)av_left : 0xffffffffu;
-            std::vector<uint16_t> before(s_sub);
-            hb_fix_entries<WPT, T>(lut, s_comp.data(), s_sub.data(), tile_lim, avail, E);
-            for (int t = 0; t < T; t++) if (before[t] != s_sub[t]) st.probes_fix += hb_sub_count(s_sub[t]);
-        }
         uint32_t o = 0;
         std::vector<uint32_t> off(T), trips(T, 0);
-        for (int t = 0; t < T; t++) { off[t] = o; o += hb_sub_count(s_sub[t]); }
-        const uint32_t nk = o;
+        for (int t = 0; t < T; t++) { off[t] = o; o += hb_sub_count(subs[(uint64_t)tile * T + t]); }
+        uint32_t nk = o;
         const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B) & 15u);
         for (int t = 0; t < T; t++) {
             const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
             const uint32_t lim = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
-            const uint32_t e = hb_sub_entry(s_sub[t]), c = hb_sub_count(s_sub[t]);
+            const uint16_t sub = subs[(uint64_t)tile * T + t];
+            const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
             if (c) {
-                if (al + off[t] + c + 1 > stage_bytes) return false;   /* staging bound violated */
+                if (al + off[t] + c > stage_bytes) return false;   /* staging bound violated */
                 uint32_t w[WPT + 1];
-                for (int j = 0; j <= WPT; j++) w[j] = W[t][j];
-                Sink sink{s_out.data() + al + off[t]};
-                uint32_t n = hb_walk_emit<WPT>(lut, w, lim, e, sink);
-                if (n != c && n != c + 1) return false;               /* record/chain mismatch */
+                load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+                /* canary right behind this thread's slice: nothing may be written there */
+                const uint8_t canary = s_out[al + off[t] + c];
+                uint32_t n = lim == S ? hb_emit_fast<WPT>(tbE, w, e, c, s_out.data() + al + off[t])
+                                      : hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, s_out.data() + al + off[t]);
+                if (n != c) return false;                          /* record/chain mismatch */
+                if (t == T - 1 || hb_sub_count(subs[(uint64_t)tile * T + t + 1]) == 0 || true)
+                    if (s_out[al + off[t] + c] != canary) return false;   /* wrote past its slice */
                 st.probes_emit += n;
                 trips[t] = n;
             }
         }
         for (int w0 = 0; w0 < T; w0 += 32)
             st.warp_iters_emit += *std::max_element(trips.begin() + w0, trips.begin() + std::min(T, w0 + 32));
+        if (B < total_valid && B + nk > total_valid) nk = (uint32_t)(total_valid - B);
+        else if (B >= total_valid) nk = 0;
         if (B + nk > out_capacity) return false;
-        /* same vector/partial split as the kernel */
         uint8_t *gbase = out + B - al;
         const uint32_t endb = al + nk, nvec = (endb + 15u) >> 4;
         for (uint32_t v = 0; v < nvec; v++) {
@@ -307,13 +282,16 @@ struct Emul {
 
 template <int WPT, int T>
 static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32_t minlen,
+               const uint32_t *stab, const uint32_t *etab, uint32_t wf,
                const uint32_t *words, uint64_t nwords, uint64_t bits_own, uint64_t bits_avail,
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats) {
     Emul<WPT, T> E;
     memset(&E.st, 0, sizeof(E.st));
     E.words = words; E.nwords = nwords; E.bits_own = bits_own; E.bits_avail = bits_avail;
-    E.lut = hb_lutref{lut_entries, lut_entries, (1u << w1) - 1u};
+    hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
+    E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
+    E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.maxlen = maxlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
@@ -328,25 +306,29 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     if (have_entry) {
         uint64_t res[4] = { 0, entry, entry, base };
         if (E.ntiles) E.scan_down(entry & 31u, base, res);
+        for (uint32_t tile = 0; tile < E.ntiles; tile++) E.fix_tile(tile);
         uint32_t S = 32u * WPT;
         uint32_t stage = ((T * ((S + minlen - 1) / minlen) + 32u) + 15u) & ~15u;
         for (uint32_t tile = 0; tile < E.ntiles; tile++)
-            if (!E.emit_tile(tile, out, out_capacity, stage)) { rc = -6; break; }
+            if (!E.emit_tile(tile, out, out_capacity, stage, res[0])) { rc = -6; break; }
         if (result) memcpy(result, res, sizeof(res));
     }
+    if (E.st.long_probes >> 63) rc = -100;   /* fast and slow word walks disagreed */
     if (stats) *stats = E.st;
     return rc;
 }
 
 extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32_t minlen,
+                        const uint32_t *stab, const uint32_t *etab, uint32_t wf,
                         const uint32_t *words, uint64_t nwords, uint64_t bits_own,
                         uint64_t bits_avail, int wpt, int T, int have_entry, uint32_t entry,
                         uint64_t base, uint8_t *out, uint64_t out_capacity, uint64_t *shard_map,
                         uint64_t *result, emul_stats *stats) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
-        return run<W, TT>(lut_entries, w1, maxlen, minlen, words, nwords, bits_own, bits_avail,  \
-                          have_entry, entry, base, out, out_capacity, shard_map, result, stats)
+        return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
+                          bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
+                          shard_map, result, stats)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

@@ -37,7 +37,8 @@ def lib():
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC,
                                    SRC, "-o", SO])
         L = C.CDLL(SO)
-        L.emul_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+        L.emul_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                               C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                C.c_void_p, C.POINTER(Stats)]
@@ -64,7 +65,10 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
     st = Stats()
     ent = np.ascontiguousarray(lut["entries"], dtype=np.uint32)
     words = np.ascontiguousarray(words, dtype=np.uint32)
-    rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"], words.ctypes.data,
+    stab = np.ascontiguousarray(lut["stab"], dtype=np.uint32)
+    etab = np.ascontiguousarray(lut["etab"], dtype=np.uint32)
+    rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"],
+                        stab.ctypes.data, etab.ctypes.data, lut["wf"], words.ctypes.data,
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
                         out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st))
     return out, smap, res, st.as_dict(), rc
