@@ -391,12 +391,12 @@ def main():
             "config": {"workload": args.workload, "description": desc, "seed": SEED,
                        "symbols_total": n_total, "compressed_bytes_total": int(nbytes_total),
                        "bits_total": int(bits_total), "max_code_length": model.maxlen,
-                       "words_per_thread": args.wpt or 4,
+                       "words_per_thread": args.wpt or 8,
                        "parallelism": f"byte-range shards x{world}, 1 NCCL all-gather of 32-entry maps" if world > 1 else "single GPU",
                        "l2": "inputs and outputs larger than L2 (no flush needed)",
                        "compressed_input_GB_per_s": in_gbs},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 5 * args.steps + (args.steps if world > 1 else 0),
+            "gpu_launches": 6 * args.steps + (args.steps if world > 1 else 0),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

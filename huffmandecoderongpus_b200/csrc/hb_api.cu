@@ -18,6 +18,7 @@ struct hb_codebook {
     hb_ctx *ctx;
     hb_lut lut;        /* host copy (entries kept for the encoder / tests) */
     uint32_t *d_lut;
+    double implied_avg_len;   /* sum over leaves of 2^-len * len */
 };
 
 struct hb_buf {
@@ -30,7 +31,7 @@ struct hb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaDeviceProp prop;
-    int wpt = 4;
+    int wpt = 8;
     int ctas_per_sm = 0;
     cudaEvent_t ev0[HB_NEV];   /* default event set */
     cudaEvent_t *ev = nullptr; /* set used by the current step */
@@ -147,7 +148,7 @@ extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_
         words_per_thread != 16)
         return HB_ERR_ARG;
     if (ctas_per_sm < 0 || ctas_per_sm > 32) return HB_ERR_ARG;
-    ctx->wpt = words_per_thread ? words_per_thread : 4;
+    ctx->wpt = words_per_thread ? words_per_thread : 8;
     ctx->ctas_per_sm = ctas_per_sm;
     return HB_OK;
 }
@@ -181,6 +182,24 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
     cb->d_lut = nullptr;
     int rc = hb_lut_build(tree, nodes, 0, 0, &cb->lut);
     if (rc != HB_OK) { delete cb; return rc; }
+    {   /* expected code length under the code's own implied distribution */
+        double acc = 0.0;
+        for (int v = 0, sp = 0; ; ) {
+            /* iterative DFS over the (validated) tree, depth kept alongside */
+            static thread_local int32_t st_node[2 * 64 + 4];
+            static thread_local int st_depth[2 * 64 + 4];
+            st_node[0] = 0; st_depth[0] = 0; sp = 1;
+            while (sp > 0) {
+                v = st_node[--sp];
+                int d = st_depth[sp];
+                if (tree[v].izero == -1) { acc += (double)d / (double)(1ull << d); continue; }
+                st_node[sp] = tree[v].izero; st_depth[sp++] = d + 1;
+                st_node[sp] = tree[v].ione;  st_depth[sp++] = d + 1;
+            }
+            break;
+        }
+        cb->implied_avg_len = acc;
+    }
     cudaSetDevice(ctx->device);
     /* device layout: [single-symbol LUT][S-table][E-table] */
     const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
@@ -233,13 +252,22 @@ static size_t emit_smem_bytes(uint32_t, uint32_t stage_bytes) {
     return sizeof(uint32_t) * 16 + stage_bytes;
 }
 
-static uint32_t stage_bytes_for(int wpt, uint32_t minlen) {
-    /* at most ceil(S / minlen) codewords start in a subsequence; + alignment
-     * shift (<16), rounded to 16 */
-    uint32_t S = 32u * (uint32_t)wpt;
-    uint32_t per = (S + minlen - 1) / minlen;
-    uint32_t b = HB_T * per + 16 + 16;
-    return (b + 15u) & ~15u;
+/* Emit-kernel staging: a window of `win` output bytes per tile pass plus one
+ * thread's worth of overhang (at most ceil(S / minlen) symbols) plus alignment.
+ * The window is sized for the output a tile produces when symbols occur with
+ * the probabilities the code table implies (avg code length = sum 2^-len * len),
+ * with 20 % headroom; more compressible tiles simply take several windows. */
+static void stage_geometry(const hb_codebook *cb, int wpt, uint32_t *win, uint32_t *stage_bytes) {
+    const uint32_t S = 32u * (uint32_t)wpt;
+    const uint32_t max_c = (S + cb->lut.minlen - 1) / cb->lut.minlen;
+    const uint32_t worst = HB_T * max_c;
+    double avg = cb->implied_avg_len > 1.0 ? cb->implied_avg_len : 1.0;
+    uint32_t typical = (uint32_t)((double)HB_T * S * 1.2 / avg) + 64;
+    uint32_t w = typical < worst ? typical : worst;
+    if (w < max_c) w = max_c;   /* a window holds at least one thread's output (emit kernel invariant) */
+    w = (w + 15u) & ~15u;
+    *win = w;
+    *stage_bytes = (w + max_c + 16u + 15u) & ~15u;
 }
 
 template <typename K>
@@ -343,13 +371,14 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     hb_stream_args ae = a;
     ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
-    uint32_t stage = stage_bytes_for(WPT, cb->lut.minlen);
+    uint32_t win = 0, stage = 0;
+    stage_geometry(cb, WPT, &win, &stage);
     size_t smem = emit_smem_bytes(a.wf, stage);
     int grid = 1;
     if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
     hb_emit_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
         ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-        (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity,
+        (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
         (uint32_t *)(misc + 36));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));

@@ -145,6 +145,16 @@ HB_HD uint32_t hb_acc_add(uint32_t acc, uint32_t ent) {   /* acc += ent >> 16 */
 #endif
 }
 
+/* ent >> 16, written so that the compiler does not fold it with the in-loop
+ * accumulate and carry a copy of the accumulator through every iteration */
+HB_HD uint32_t hb_hi16(uint32_t ent) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(ent, 0u, 0x4432);
+#else
+    return ent >> 16;
+#endif
+}
+
 HB_HD uint32_t hb_fast_load(const hb_tables &tb, uint32_t lo2, uint32_t hi2, uint32_t acc) {
     uint32_t x = hb_funnel_r(lo2, hi2, acc) & tb.fmask4;
 #ifdef __CUDA_ARCH__
@@ -169,7 +179,7 @@ HB_HD void hb_word_fast(const hb_tables &tb, uint32_t lo, uint32_t hi, uint32_t 
             ent = hb_fast_load(tb, lo2, hi2, acc);
             acc = hb_acc_add(acc, ent);
         } while (!(acc & 0xE0u));
-        prev = acc - (ent >> 16);       /* state before the last probe */
+        prev = acc - hb_hi16(ent);      /* state before the last probe */
         if ((acc & 0xffu) < HB_FAST_MARK) break;
         /* a codeword longer than the table index starts at prev's position */
         uint32_t sym;
@@ -256,13 +266,26 @@ HB_HD bool hb_rewalk(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t
     return !merged;
 }
 
+/* staging-buffer handle: a shared-state-space byte address on the device (a
+ * generic pointer would make every store rebuild the shared window base), a
+ * plain pointer in the host emulation */
+#ifdef __CUDA_ARCH__
+typedef uint32_t hb_out_t;
+__device__ __forceinline__ void hb_st8(hb_out_t base, uint32_t idx, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + idx), "r"(v));
+}
+#else
+typedef uint8_t *hb_out_t;
+static inline void hb_st8(hb_out_t base, uint32_t idx, uint32_t v) { base[idx] = (uint8_t)v; }
+#endif
+
 /* ==== emit walks: decode the chain of entry e and store its symbols ==========
  * E-table probes carry up to two symbols.  The second symbol of the last probe
  * of the LAST word may start in the next subsequence; it is stored only while
  * its index is below c, the chain's symbol count known from the sync kernel. */
 template <int WPT>
 HB_HD uint32_t hb_emit_fast(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
-                            uint32_t c, uint8_t *out) {
+                            uint32_t c, hb_out_t out) {
     uint32_t acc = e;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
@@ -273,16 +296,16 @@ HB_HD uint32_t hb_emit_fast(const hb_tables &tb, const uint32_t (&w)[WPT + 1], u
             do {
                 ent = hb_fast_load(tb, lo2, hi2, acc);
                 const uint32_t n = acc >> 8;
-                out[n] = (uint8_t)ent;
-                if (j < WPT - 1) { if (ent & (2u << 24)) out[n + 1] = (uint8_t)(ent >> 8); }
-                else { if ((ent & (2u << 24)) && n + 1 < c) out[n + 1] = (uint8_t)(ent >> 8); }
+                hb_st8(out, n, ent);
+                if (j < WPT - 1) { if (ent & (2u << 24)) hb_st8(out, n + 1, ent >> 8); }
+                else { if ((ent & (2u << 24)) && n + 1 < c) hb_st8(out, n + 1, ent >> 8); }
                 acc = hb_acc_add(acc, ent);
             } while (!(acc & 0xE0u));
-            prev = acc - (ent >> 16);
+            prev = acc - hb_hi16(ent);
             if ((acc & 0xffu) < HB_FAST_MARK) break;
             uint32_t sym;
             uint32_t len = hb_probe(tb.slow, lo, hi, prev & 0xffu, &sym);
-            out[prev >> 8] = (uint8_t)sym;
+            hb_st8(out, prev >> 8, sym);
             acc = prev + len + 0x100u;
             if (acc & 0xE0u) break;
         }
@@ -293,7 +316,7 @@ HB_HD uint32_t hb_emit_fast(const hb_tables &tb, const uint32_t (&w)[WPT + 1], u
 
 template <int WPT>
 HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], uint32_t lim,
-                            uint32_t e, uint32_t c, uint8_t *out) {
+                            uint32_t e, uint32_t c, hb_out_t out) {
     uint32_t pos = e, n = 0;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
@@ -301,7 +324,7 @@ HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], 
         while (pos < limj) {
             uint32_t sym;
             pos += hb_probe(lut, w[j], w[j + 1], pos, &sym);
-            if (n < c) out[n] = (uint8_t)sym;
+            if (n < c) hb_st8(out, n, sym);
             n++;
         }
     }

@@ -28,6 +28,9 @@
 #include "hb_core.cuh"
 
 #define HB_T 256            /* threads per CTA = subsequences per tile */
+#ifndef HB_SYNC_MIN_CTAS
+#define HB_SYNC_MIN_CTAS 6  /* register budget of the sync kernel: 65536 / (6 * 256) = 42 */
+#endif
 #define HB_SCAN_T 1024      /* threads per CTA of the scan kernels (32 warps x 32 tiles) */
 
 struct hb_stream_args {
@@ -46,6 +49,14 @@ struct hb_stream_args {
 /* fast-table footprint in shared memory, kept a multiple of 16 bytes */
 __host__ __device__ __forceinline__ uint32_t hb_lut_smem_words(uint32_t wf) {
     return ((1u << wf) + 3u) & ~3u;
+}
+
+/* Launder a shared-space address through an empty asm so that the compiler keeps
+ * it in a register instead of re-deriving it (S2UR SR_CgaCtaId + ULEA) inside
+ * the probe loops. */
+__device__ __forceinline__ uint32_t hb_opaque(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
 }
 
 /* device status word bits */
@@ -101,7 +112,7 @@ __device__ __forceinline__ uint32_t hb_block_exscan(uint32_t v, uint32_t *s_warp
 
 /* ------------------------------------------------------------------------- */
 template <int WPT>
-__global__ void __launch_bounds__(HB_T)
+__global__ void __launch_bounds__(HB_T, HB_SYNC_MIN_CTAS)
 hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
@@ -119,7 +130,7 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
     __syncthreads();
     hb_tables tb;
     tb.fast = s_fast;
-    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
 
@@ -372,7 +383,7 @@ hb_fix_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry, uint16_t
     __syncthreads();
     hb_tables tb;
     tb.fast = s_fast;
-    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
     const uint32_t tile = blockIdx.x * T + threadIdx.x;
@@ -390,7 +401,7 @@ template <int WPT>
 __global__ void __launch_bounds__(HB_T)
 hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
-               uint64_t out_capacity, uint32_t *__restrict__ status) {
+               uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
@@ -404,10 +415,11 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     __syncthreads();
     hb_tables tb;
     tb.fast = s_fast;
-    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
     const uint64_t total_valid = result[0];
+    const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
 
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
@@ -420,39 +432,60 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
         const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
         uint32_t nk;
         const uint32_t o = hb_block_exscan(c, s_warp, &nk);
-
         const uint32_t lim = sub0 >= a.bits_own ? 0u
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
-        const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B) & 15u);
-        if (c) {
-            if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, s_out + al + o);
-            else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, s_out + al + o);
-        }
-        __syncthreads();
-
-        /* staging -> global: s_out[al + i] -> out[B + i], 16-byte vectors aligned
-         * in both spaces, partial first/last vectors byte-wise */
-        if (B < total_valid && B + nk > total_valid) nk = (uint32_t)(total_valid - B);
-        else if (B >= total_valid) nk = 0;
-        if (B + nk > out_capacity) {
+        /* symbols past the shard's valid total (a cut-off last codeword) are not written */
+        uint32_t nvalid = nk;
+        if (B >= total_valid) nvalid = 0;
+        else if (B + nk > total_valid) nvalid = (uint32_t)(total_valid - B);
+        if (B + nvalid > out_capacity) {
             if (t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
-        } else {
-            uint8_t *gbase = out + B - al;     /* 16-byte aligned */
-            const uint32_t endb = al + nk;
-            const uint32_t nvec = (endb + 15u) >> 4;
-            for (uint32_t v = t; v < nvec; v += T) {
-                const uint32_t b0 = v << 4;
-                if (b0 >= al && b0 + 16u <= endb) {
-                    *reinterpret_cast<uint4 *>(gbase + b0) =
-                        *reinterpret_cast<const uint4 *>(s_out + b0);
-                } else {
-                    const uint32_t lo = b0 < al ? al : b0;
-                    const uint32_t hi = b0 + 16u < endb ? b0 + 16u : endb;
-                    for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
+            __syncthreads();
+            continue;
+        }
+
+        /* The staging buffer holds `win` bytes of tile output plus one thread's
+         * worth of overhang; a tile whose output is larger (data far more
+         * compressible than the code table suggests) is emitted in several
+         * windows.  Window p takes the threads whose first byte lies in
+         * [p*win, (p+1)*win); their slices are contiguous, so it copies out
+         * [end of window p-1's threads, end of its own threads). */
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+            const bool mine = c && o >= wb && o - wb < win;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
+            if (t == 0) s_warp[15] = nk;                     /* default: last window */
+            __syncthreads();
+            if (mine) {
+                const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
+                if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, dst);
+                else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
+                if (o + c - wb >= win && o + c < nk) s_warp[15] = o + c;   /* I am the window's last thread */
+            }
+            __syncthreads();
+            uint32_t hi_b = s_warp[15];
+            if (hi_b > nvalid) hi_b = nvalid;
+            if (lo_b < hi_b) {
+                /* staging -> global: s_out[al + (b - wb)] -> out[B + b], 16-byte vectors
+                 * aligned in both spaces, partial first/last vectors byte-wise */
+                uint8_t *gbase = out + B + wb - al;          /* 16-byte aligned */
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t v0 = begb >> 4, nvec = (endb + 15u) >> 4;
+                for (uint32_t v = v0 + t; v < nvec; v += T) {
+                    const uint32_t b0 = v << 4;
+                    if (b0 >= begb && b0 + 16u <= endb) {
+                        *reinterpret_cast<uint4 *>(gbase + b0) =
+                            *reinterpret_cast<const uint4 *>(s_out + b0);
+                    } else {
+                        const uint32_t lo = b0 < begb ? begb : b0;
+                        const uint32_t hi = b0 + 16u < endb ? b0 + 16u : endb;
+                        for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
+                    }
                 }
             }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

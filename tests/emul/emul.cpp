@@ -232,50 +232,61 @@ struct Emul {
     }
 
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
-    bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t stage_bytes, uint64_t total_valid) {
+    bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
+                   uint64_t total_valid) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t B = tile_base[tile];
-        std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
-        uint32_t o = 0;
-        std::vector<uint32_t> off(T), trips(T, 0);
-        for (int t = 0; t < T; t++) { off[t] = o; o += hb_sub_count(subs[(uint64_t)tile * T + t]); }
-        uint32_t nk = o;
-        const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B) & 15u);
-        for (int t = 0; t < T; t++) {
-            const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
-            const uint32_t lim = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
-            const uint16_t sub = subs[(uint64_t)tile * T + t];
-            const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
-            if (c) {
-                if (al + off[t] + c > stage_bytes) return false;   /* staging bound violated */
+        uint32_t o_acc = 0;
+        std::vector<uint32_t> off(T), cnt(T), trips(T, 0);
+        for (int t = 0; t < T; t++) { off[t] = o_acc; cnt[t] = hb_sub_count(subs[(uint64_t)tile * T + t]); o_acc += cnt[t]; }
+        const uint32_t nk = o_acc;
+        uint32_t nvalid = nk;
+        if (B >= total_valid) nvalid = 0;
+        else if (B + nk > total_valid) nvalid = (uint32_t)(total_valid - B);
+        if (B + nvalid > out_capacity) return false;
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+            std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
+            uint32_t hi_b = nk;
+            for (int t = 0; t < T; t++) {
+                const uint32_t o = off[t], c = cnt[t];
+                const bool mine = c && o >= wb && o - wb < win;
+                if (!mine) continue;
+                const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+                const uint32_t lim = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
+                const uint32_t e = hb_sub_entry(subs[(uint64_t)tile * T + t]);
+                if (al + (o - wb) + c > stage_bytes) return false;      /* staging bound violated */
                 uint32_t w[WPT + 1];
                 load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-                /* canary right behind this thread's slice: nothing may be written there */
-                const uint8_t canary = s_out[al + off[t] + c];
-                uint32_t n = lim == S ? hb_emit_fast<WPT>(tbE, w, e, c, s_out.data() + al + off[t])
-                                      : hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, s_out.data() + al + off[t]);
-                if (n != c) return false;                          /* record/chain mismatch */
-                if (t == T - 1 || hb_sub_count(subs[(uint64_t)tile * T + t + 1]) == 0 || true)
-                    if (s_out[al + off[t] + c] != canary) return false;   /* wrote past its slice */
+                uint8_t *dst = s_out.data() + al + (o - wb);
+                const uint8_t canary = dst[c];
+                uint32_t n = lim == S ? hb_emit_fast<WPT>(tbE, w, e, c, dst)
+                                      : hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
+                if (n != c) return false;                                /* record/chain mismatch */
+                if (dst[c] != canary) return false;                      /* wrote past its slice */
                 st.probes_emit += n;
                 trips[t] = n;
+                if (o + c - wb >= win && o + c < nk) hi_b = o + c;
             }
+            if (hi_b > nvalid) hi_b = nvalid;
+            if (lo_b < hi_b) {
+                uint8_t *gbase = out + B + wb - al;
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t v0 = begb >> 4, nvec = (endb + 15u) >> 4;
+                for (uint32_t v = v0; v < nvec; v++) {
+                    const uint32_t b0 = v << 4;
+                    if (b0 >= begb && b0 + 16u <= endb) memcpy(gbase + b0, s_out.data() + b0, 16);
+                    else {
+                        const uint32_t lo = b0 < begb ? begb : b0, hi = b0 + 16u < endb ? b0 + 16u : endb;
+                        for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
+                    }
+                }
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
         }
         for (int w0 = 0; w0 < T; w0 += 32)
             st.warp_iters_emit += *std::max_element(trips.begin() + w0, trips.begin() + std::min(T, w0 + 32));
-        if (B < total_valid && B + nk > total_valid) nk = (uint32_t)(total_valid - B);
-        else if (B >= total_valid) nk = 0;
-        if (B + nk > out_capacity) return false;
-        uint8_t *gbase = out + B - al;
-        const uint32_t endb = al + nk, nvec = (endb + 15u) >> 4;
-        for (uint32_t v = 0; v < nvec; v++) {
-            const uint32_t b0 = v << 4;
-            if (b0 >= al && b0 + 16u <= endb) memcpy(gbase + b0, s_out.data() + b0, 16);
-            else {
-                const uint32_t lo = b0 < al ? al : b0, hi = b0 + 16u < endb ? b0 + 16u : endb;
-                for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
-            }
-        }
         return true;
     }
 };
@@ -285,7 +296,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                const uint32_t *stab, const uint32_t *etab, uint32_t wf,
                const uint32_t *words, uint64_t nwords, uint64_t bits_own, uint64_t bits_avail,
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
-               uint64_t *shard_map, uint64_t *result, emul_stats *stats) {
+               uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win) {
     Emul<WPT, T> E;
     memset(&E.st, 0, sizeof(E.st));
     E.words = words; E.nwords = nwords; E.bits_own = bits_own; E.bits_avail = bits_avail;
@@ -308,9 +319,12 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
         if (E.ntiles) E.scan_down(entry & 31u, base, res);
         for (uint32_t tile = 0; tile < E.ntiles; tile++) E.fix_tile(tile);
         uint32_t S = 32u * WPT;
-        uint32_t stage = ((T * ((S + minlen - 1) / minlen) + 32u) + 15u) & ~15u;
+        uint32_t max_c = (S + minlen - 1) / minlen;
+        uint32_t win = emit_win ? emit_win : ((T * max_c + 15u) & ~15u);   /* 0 = worst case, one window */
+        if (win < ((max_c + 15u) & ~15u)) win = (max_c + 15u) & ~15u;      /* a window holds at least one thread's output */
+        uint32_t stage = (win + max_c + 16u + 15u) & ~15u;
         for (uint32_t tile = 0; tile < E.ntiles; tile++)
-            if (!E.emit_tile(tile, out, out_capacity, stage, res[0])) { rc = -6; break; }
+            if (!E.emit_tile(tile, out, out_capacity, win, stage, res[0])) { rc = -6; break; }
         if (result) memcpy(result, res, sizeof(res));
     }
     if (E.st.long_probes >> 63) rc = -100;   /* fast and slow word walks disagreed */
@@ -323,12 +337,12 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         const uint32_t *words, uint64_t nwords, uint64_t bits_own,
                         uint64_t bits_avail, int wpt, int T, int have_entry, uint32_t entry,
                         uint64_t base, uint8_t *out, uint64_t out_capacity, uint64_t *shard_map,
-                        uint64_t *result, emul_stats *stats) {
+                        uint64_t *result, emul_stats *stats, uint32_t emit_win) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
-                          shard_map, result, stats)
+                          shard_map, result, stats, emit_win)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

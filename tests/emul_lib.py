@@ -41,7 +41,7 @@ def lib():
                                C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
-                               C.c_void_p, C.POINTER(Stats)]
+                               C.c_void_p, C.POINTER(Stats), C.c_uint32]
         _lib = L
     return _lib
 
@@ -55,7 +55,7 @@ def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
 
 
 def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=True,
-        out_capacity=None, out_offset=0):
+        out_capacity=None, out_offset=0, emit_win=0):
     """Returns (out bytes, shard_map[32], result[4], stats dict, rc)."""
     cap = int(out_capacity if out_capacity is not None else bits_own + 64)
     raw = np.zeros(cap + 64 + out_offset, dtype=np.uint8)
@@ -70,7 +70,7 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
     rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"],
                         stab.ctypes.data, etab.ctypes.data, lut["wf"], words.ctypes.data,
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
-                        out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st))
+                        out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win)
     return out, smap, res, st.as_dict(), rc
 
 

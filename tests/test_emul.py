@@ -164,3 +164,21 @@ def test_output_alignment_offsets():
         out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, out_offset=off)
         assert rc == 0 and np.array_equal(out[: want.size], want)
         assert not out[want.size:].any()  # nothing written past the end
+
+
+@pytest.mark.parametrize("shape,win", [((4, 256), 4096), ((4, 256), 1008), ((8, 256), 2048), ((2, 8), 16), ((1, 4), 16)])
+def test_emit_in_several_windows(shape, win):
+    """A staging buffer smaller than a tile's output (data more compressible than
+    the code table suggests): the emit kernel's window loop must stitch the tile
+    back together exactly."""
+    for name in ("paper1", "ecoli"):
+        st = _stream(name)
+        if name == "ecoli" and shape[1] < 256:
+            continue
+        lut = hb.build_lut(st.tree)
+        w = E.words_of(st.data, st.nbytes)
+        for off in (0, 5):
+            out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_win=win, out_offset=off)
+            assert rc == 0 and int(res[0]) == st.usize
+            assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
+            assert not out[st.usize:].any()
