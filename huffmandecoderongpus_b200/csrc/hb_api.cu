@@ -45,8 +45,12 @@ struct hb_ctx {
     bool have_map = false;
     uint32_t map_ntiles = 0, map_ncta = 0;
     int map_wpt = 0;
-    /* host-buffer path */
+    /* host-buffer path: device buffers and the last code table are kept across
+     * calls (the reference harness calls an approach 26 times with the same tree) */
     hb_buf d_comp, d_out;
+    hb_codebook *host_cb = nullptr;
+    hb_node_abi *host_tree = nullptr;
+    int host_nodes = 0;
     uint64_t *h_res = nullptr; /* pinned, 8 words */
 };
 
@@ -134,6 +138,8 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     hb_buf *bufs[] = { &ctx->subs, &ctx->tmaps, &ctx->wmaps, &ctx->cmaps, &ctx->cprefix,
                        &ctx->tile_entry, &ctx->tile_base, &ctx->misc, &ctx->d_comp, &ctx->d_out };
     for (hb_buf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->host_cb) hb_codebook_destroy(ctx->host_cb);
+    free(ctx->host_tree);
     for (int i = 0; i < HB_NEV; i++) cudaEventDestroy(ctx->ev0[i]);
     for (int i = 0; i < ctx->tim_cap * HB_NEV; i++) cudaEventDestroy(ctx->tim_ev[i]);
     free(ctx->tim_ev);
@@ -306,6 +312,7 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
     a->lut = cb->d_lut;
     a->w1 = cb->lut.w1;
     a->maxlen = cb->lut.maxlen;
+    a->minlen = cb->lut.minlen;
     a->fast = cb->d_lut + cb->lut.n_entries;   /* S-table; the E-table follows it */
     a->wf = cb->lut.wf;
     return HB_OK;
@@ -364,8 +371,12 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
         (uint64_t *)ctx->tile_base.p, misc + 32, a.bits_own, a.bits_avail);
     CK(cudaGetLastError());
     {   /* re-chain the head of every tile whose true entry offset is not 0 (S-table) */
-        hb_fix_kernel<WPT><<<(a.ntiles + HB_T - 1) / HB_T, HB_T, 0, ctx->stream>>>(
-            a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
+        if (a.minlen == a.maxlen)
+            hb_fix_fixed_kernel<WPT><<<a.ntiles, HB_T, 0, ctx->stream>>>(
+                a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
+        else
+            hb_fix_kernel<WPT><<<(a.ntiles + HB_T - 1) / HB_T, HB_T, 0, ctx->stream>>>(
+                a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -519,9 +530,30 @@ extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
     hb_result local;
     if (!res) res = &local;
     CK(cudaSetDevice(ctx->device));
-    hb_codebook *cb = nullptr;
-    int rc = hb_codebook_create(ctx, tree, nodes, &cb);
-    if (rc) return rc;
+    int rc = HB_OK;
+    {   /* reuse the cached code table when the tree is the same, field by field */
+        bool same = ctx->host_cb && ctx->host_nodes == nodes;
+        for (int i = 0; same && i < nodes; i++)
+            same = tree[i].sym == ctx->host_tree[i].sym && tree[i].izero == ctx->host_tree[i].izero &&
+                   tree[i].ione == ctx->host_tree[i].ione;
+        if (!same) {
+            if (ctx->host_cb) { hb_codebook_destroy(ctx->host_cb); ctx->host_cb = nullptr; }
+            free(ctx->host_tree);
+            ctx->host_tree = nullptr;
+            ctx->host_nodes = 0;
+            rc = hb_codebook_create(ctx, tree, nodes, &ctx->host_cb);
+            if (rc) return rc;
+            ctx->host_tree = (hb_node_abi *)malloc(sizeof(hb_node_abi) * (size_t)nodes);
+            if (!ctx->host_tree) { hb_codebook_destroy(ctx->host_cb); ctx->host_cb = nullptr; return HB_ERR_NOMEM; }
+            for (int i = 0; i < nodes; i++) {
+                ctx->host_tree[i].sym = tree[i].sym;
+                ctx->host_tree[i].izero = tree[i].izero;
+                ctx->host_tree[i].ione = tree[i].ione;
+            }
+            ctx->host_nodes = nodes;
+        }
+    }
+    hb_codebook *cb = ctx->host_cb;
     const uint64_t nbytes = (bits + 7) / 8;
     const uint64_t padded = (nbytes + 15) & ~15ull;
     do {
@@ -540,7 +572,6 @@ extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
             if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "download"); break; }
         }
     } while (0);
-    hb_codebook_destroy(cb);
     return rc;
 }
 

@@ -279,6 +279,20 @@ typedef uint8_t *hb_out_t;
 static inline void hb_st8(hb_out_t base, uint32_t idx, uint32_t v) { base[idx] = (uint8_t)v; }
 #endif
 
+/* ==== fixed-length codes (minlen == maxlen == len) ===========================
+ * Such codes never self-synchronise (the reference's E.coli corpus: four 2-bit
+ * codes), so chains of different entry offsets never merge; but every chain is
+ * an arithmetic progression, and entry offsets, counts and exits follow in
+ * closed form.  first start at or after bit position p of the chain e, e+len,..: */
+HB_HD uint32_t hb_fixed_next(uint32_t e, uint32_t len, uint32_t p) {
+    return p <= e ? e : e + ((p - e + len - 1u) / len) * len;
+}
+/* number of starts of that chain in [lo, hi) */
+HB_HD uint32_t hb_fixed_count(uint32_t e, uint32_t len, uint32_t lo, uint32_t hi) {
+    const uint32_t a = hb_fixed_next(e, len, lo);
+    return a >= hi ? 0u : (hi - a + len - 1u) / len;
+}
+
 /* ==== emit walks: decode the chain of entry e and store its symbols ==========
  * E-table probes carry up to two symbols.  The second symbol of the last probe
  * of the LAST word may start in the next subsequence; it is stored only while

@@ -42,6 +42,7 @@ struct hb_stream_args {
     const uint32_t *lut;     /* single-symbol multi-level LUT in global memory */
     uint32_t w1;             /* its level-1 width */
     uint32_t maxlen;         /* number of candidate entry offsets to resolve */
+    uint32_t minlen;         /* == maxlen: fixed-length code, closed-form chains */
     const uint32_t *fast;    /* S-table (sync kernel) or E-table (emit kernel), 1 << wf entries */
     uint32_t wf;
 };
@@ -134,6 +135,7 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
 
+    const bool fixed_len = a.minlen == a.maxlen;
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
@@ -146,10 +148,11 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
         const uint32_t lim = sub0 >= a.bits_own ? 0u
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
 
-        /* chain of the guess "a codeword starts at offset 0 of my subsequence" */
+        /* chain of the guess "a codeword starts at offset 0 of my subsequence"
+         * (for a fixed-length code the exact offset under tile entry 0 is known) */
         uint32_t rec[WPT];
-        uint32_t e = 0;
-        hb_walk<WPT>(tb, w, lim, 0u, rec);
+        uint32_t e = fixed_len ? hb_fixed_next(0u, a.maxlen, (uint32_t)t * S) - (uint32_t)t * S : 0u;
+        hb_walk<WPT>(tb, w, lim, e, rec);
         s_land[t] = hb_rec_land(rec[WPT - 1]);
         __syncthreads();
 
@@ -191,8 +194,14 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
             const uint32_t wl = (tile_lim - 1u) >> 5;           /* last owned word */
             const uint32_t X0 = hb_rec_land(s_rec[(wl % WPT) * T + wl / WPT]);
             uint32_t m = hb_map_pack32(X0, C0);
-            if (t > 0 && (uint32_t)t < a.maxlen)
-                m = hb_hyp_walk<WPT, T>(tb, s_comp, s_rec, s_cs, C0, X0, tile_lim, (uint32_t)t);
+            if (t > 0 && (uint32_t)t < a.maxlen) {
+                if (fixed_len) {   /* never merges: arithmetic progression t, t+len, ... */
+                    const uint32_t n = hb_fixed_count((uint32_t)t, a.maxlen, 0u, tile_lim);
+                    m = hb_map_pack32((hb_fixed_next((uint32_t)t, a.maxlen, tile_lim) - tile_lim) & 31u, n);
+                } else {
+                    m = hb_hyp_walk<WPT, T>(tb, s_comp, s_rec, s_cs, C0, X0, tile_lim, (uint32_t)t);
+                }
+            }
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
         __syncthreads();
@@ -394,6 +403,28 @@ hb_fix_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry, uint16_t
     const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
     hb_tile_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
     hb_fix_entries<WPT, T>(tb, word, subs + (uint64_t)tile * T, tile_lim, E);
+}
+
+/* Fixed-length codes: the chain of the tile's true entry offset never meets the
+ * recorded one, but every subsequence's (entry, count) follows arithmetically.
+ * One thread per subsequence. */
+template <int WPT>
+__global__ void __launch_bounds__(HB_T)
+hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
+                    uint16_t *__restrict__ subs) {
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t TS = HB_T * S;
+    const uint32_t tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t E = tile_entry[tile];
+    if (E == 0) return;
+    const uint64_t own_left = a.bits_own - (uint64_t)tile * TS;
+    const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+    const uint32_t s0 = t * S;
+    if (s0 >= tile_lim) return;
+    const uint32_t s1 = tile_lim - s0 < S ? tile_lim : s0 + S;
+    const uint32_t first = hb_fixed_next(E, a.maxlen, s0);
+    subs[(uint64_t)tile * HB_T + t] =
+        hb_sub_pack((first - s0) & 31u, hb_fixed_count(E, a.maxlen, s0, s1));
 }
 
 /* ------------------------------------------------------------------------- */

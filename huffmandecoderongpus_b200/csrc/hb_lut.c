@@ -195,7 +195,7 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
  * table fits shared memory, and the sync kernel's variant carries the start
  * offsets instead of the symbols. */
 static int build_fast_tables(const hb_node *tree, hb_lut *out) {
-    uint32_t wf = out->maxlen < HB_WF_MAX ? out->maxlen : HB_WF_MAX;
+    uint32_t wf = HB_WF_MAX;   /* always full width: short codes then yield several symbols per probe */
     uint32_t n = 1u << wf;
     out->wf = wf;
     out->stab = (uint32_t *)malloc(sizeof(uint32_t) * n);

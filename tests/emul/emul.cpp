@@ -43,7 +43,7 @@ struct Emul {
     static constexpr uint32_t TS = T * S;
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
-    hb_tables tbS, tbE; uint32_t maxlen;
+    hb_tables tbS, tbE; uint32_t maxlen, minlen;
     std::vector<uint16_t> subs;
     std::vector<uint32_t> tmaps;
     std::vector<uint64_t> wmaps, cmaps, cprefix;
@@ -77,10 +77,12 @@ struct Emul {
             if (t == T - 1) s_comp[T * WPT] = w[WPT];
             const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
             lim[t] = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
-            hb_walk<WPT>(tbS, w, lim[t], 0u, rec);
+            const bool fixed_len = minlen == maxlen;
+            e[t] = fixed_len ? hb_fixed_next(0u, maxlen, (uint32_t)t * S) - (uint32_t)t * S : 0u;
+            hb_walk<WPT>(tbS, w, lim[t], e[t], rec);
             /* cross-check: the multi-symbol walk equals the symbol-by-symbol walk */
             if (lim[t] == S) {
-                uint32_t acc = 0;
+                uint32_t acc = e[t];
                 for (int j = 0; j < WPT; j++) {
                     uint32_t land, cnt;
                     hb_word_slow(tbS.slow, w[j], w[j + 1], 32u, acc, land, cnt);
@@ -143,7 +145,12 @@ struct Emul {
         for (uint32_t t = 0; t < 32; t++) {
             uint32_t m = hb_map_pack32(X0, C0);
             if (t > 0 && t < maxlen) {
-                m = hb_hyp_walk<WPT, T>(tbS, s_comp.data(), s_rec.data(), s_cs.data(), C0, X0, tile_lim, t);
+                if (minlen == maxlen) {
+                    const uint32_t n = hb_fixed_count(t, maxlen, 0u, tile_lim);
+                    m = hb_map_pack32((hb_fixed_next(t, maxlen, tile_lim) - tile_lim) & 31u, n);
+                } else {
+                    m = hb_hyp_walk<WPT, T>(tbS, s_comp.data(), s_rec.data(), s_cs.data(), C0, X0, tile_lim, t);
+                }
                 if ((m & 31u) != X0) st.hyp_unmerged++;
             }
             tmaps[(uint64_t)tile * 32 + t] = m;
@@ -226,6 +233,15 @@ struct Emul {
         const uint64_t base = (uint64_t)tile * (T * WPT);
         auto word = [&](uint32_t i) -> uint32_t { return base + i < nwords ? words[base + i] : 0u; };
         std::vector<uint16_t> before(subs.begin() + (size_t)tile * T, subs.begin() + (size_t)(tile + 1) * T);
+        if (minlen == maxlen) {   /* mirrors hb_fix_fixed_kernel */
+            for (uint32_t t = 0; t < (uint32_t)T; t++) {
+                const uint32_t s0 = t * S;
+                if (s0 >= tile_lim) break;
+                const uint32_t s1 = tile_lim - s0 < S ? tile_lim : s0 + S;
+                const uint32_t first = hb_fixed_next(E, maxlen, s0);
+                subs[(size_t)tile * T + t] = hb_sub_pack((first - s0) & 31u, hb_fixed_count(E, maxlen, s0, s1));
+            }
+        } else
         hb_fix_entries<WPT, T>(tbS, word, subs.data() + (size_t)tile * T, tile_lim, E);
         for (int t = 0; t < T; t++)
             if (before[t] != subs[(size_t)tile * T + t]) st.probes_fix += hb_sub_count(subs[(size_t)tile * T + t]);
@@ -303,7 +319,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
-    E.maxlen = maxlen;
+    E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
     E.subs.assign((size_t)E.ntiles * T, 0);
