@@ -101,6 +101,7 @@ def lib():
     L.hb_ctx_destroy.restype = None
     L.hb_ctx_configure.argtypes = [vp, i32, i32]
     L.hb_ctx_sync.argtypes = [vp]
+    L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
     L.hb_ctx_timing_begin.argtypes = [vp, i32]
     L.hb_ctx_timing_collect.argtypes = [vp, C.POINTER(C.c_double * 4), C.POINTER(i32)]
     L.hb_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(u64)]
@@ -253,6 +254,9 @@ class Context:
 
     def configure(self, words_per_thread=0, ctas_per_sm=0):
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
+
+    def set_host_chunk(self, nbytes):
+        _check(lib().hb_ctx_set_host_chunk(self.h, nbytes), "hb_ctx_set_host_chunk")
 
     def sync(self):
         _check(lib().hb_ctx_sync(self.h), "hb_ctx_sync", self.h)

@@ -51,6 +51,14 @@ struct hb_ctx {
     hb_codebook *host_cb = nullptr;
     hb_node_abi *host_tree = nullptr;
     int host_nodes = 0;
+    /* pipelined host path: copy streams, per-chunk events, pinned staging */
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t *pipe_ev = nullptr;   /* 2 per chunk: upload done, emit done */
+    int pipe_cap = 0;
+    uint64_t *h_pipe = nullptr;       /* pinned: 32 map words + 4 entry/base words per chunk */
+    hb_buf d_eb;
+    uint64_t pipe_chunk_bytes = 32ull << 20;
+    cudaEvent_t pipe_t0 = nullptr, pipe_t1 = nullptr;
     uint64_t *h_res = nullptr; /* pinned, 8 words */
 };
 
@@ -140,6 +148,13 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     for (hb_buf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->host_cb) hb_codebook_destroy(ctx->host_cb);
     free(ctx->host_tree);
+    for (int i = 0; i < 2 * ctx->pipe_cap; i++) cudaEventDestroy(ctx->pipe_ev[i]);
+    free(ctx->pipe_ev);
+    if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+    if (ctx->pipe_t0) { cudaEventDestroy(ctx->pipe_t0); cudaEventDestroy(ctx->pipe_t1); }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->d_eb.p) cudaFree(ctx->d_eb.p);
     for (int i = 0; i < HB_NEV; i++) cudaEventDestroy(ctx->ev0[i]);
     for (int i = 0; i < ctx->tim_cap * HB_NEV; i++) cudaEventDestroy(ctx->tim_ev[i]);
     free(ctx->tim_ev);
@@ -156,6 +171,12 @@ extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_
     if (ctas_per_sm < 0 || ctas_per_sm > 32) return HB_ERR_ARG;
     ctx->wpt = words_per_thread ? words_per_thread : 8;
     ctx->ctas_per_sm = ctas_per_sm;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_set_host_chunk(hb_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return HB_ERR_ARG;
+    ctx->pipe_chunk_bytes = bytes ? bytes : (32ull << 20);
     return HB_OK;
 }
 
@@ -523,6 +544,113 @@ extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *
     return hb_shard_emit(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr, d_out, out_capacity, res);
 }
 
+/* Large host-resident streams: the compressed bytes are cut into chunks (byte-range
+ * shards on ONE GPU).  All uploads are queued on a copy stream; chunk k is mapped
+ * as soon as it has landed, its 32-entry map is read back (256 B, the only host
+ * synchronisation per chunk), the host composes the entry offset / output base,
+ * the chunk is emitted and its bytes are downloaded on a second copy stream --
+ * so upload k+1, decode k and download k-1 overlap on the two PCIe directions. */
+static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t *data, uint64_t bits,
+                                     uint8_t *out, uint64_t out_capacity, hb_result *res);
+
+static int decode_host_pipelined(hb_ctx *ctx, hb_codebook *cb, const uint8_t *data, uint64_t bits,
+                                 uint8_t *out, uint64_t out_capacity, hb_result *res) {
+    int rc = decode_host_pipelined_run(ctx, cb, data, bits, out, out_capacity, res);
+    if (rc != HB_OK) {
+        /* copies may still be in flight to/from the caller's buffers: drain them
+         * before the error is reported */
+        if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t *data, uint64_t bits,
+                                     uint8_t *out, uint64_t out_capacity, hb_result *res) {
+    const uint64_t nbytes = (bits + 7) / 8;
+    const uint64_t tile_bytes = (uint64_t)HB_T * 4u * (uint64_t)ctx->wpt;
+    uint64_t cbytes = ctx->pipe_chunk_bytes / tile_bytes * tile_bytes;
+    if (cbytes < tile_bytes) cbytes = tile_bytes;
+    const int K = (int)((nbytes + cbytes - 1) / cbytes);
+    int rc;
+    if (!ctx->s_h2d) CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    if (!ctx->s_d2h) CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    if (!ctx->pipe_t0) { CK(cudaEventCreate(&ctx->pipe_t0)); CK(cudaEventCreate(&ctx->pipe_t1)); }
+    if (K > ctx->pipe_cap) {
+        cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->pipe_ev, sizeof(cudaEvent_t) * 2 * (size_t)K);
+        if (!ne) return HB_ERR_NOMEM;
+        ctx->pipe_ev = ne;
+        for (int i = 2 * ctx->pipe_cap; i < 2 * K; i++)
+            CK(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+        if (ctx->h_pipe) CK(cudaFreeHost(ctx->h_pipe));
+        ctx->h_pipe = nullptr;
+        ctx->pipe_cap = K;
+        CK(cudaMallocHost((void **)&ctx->h_pipe, sizeof(uint64_t) * 36 * (size_t)K));
+    }
+    if ((rc = ensure(ctx, ctx->d_eb, sizeof(uint64_t) * 4 * (size_t)K))) return rc;
+    const uint64_t padded = (nbytes + 15) & ~15ull;
+    if ((rc = ensure(ctx, ctx->d_comp, padded + 32))) return rc;
+    if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) return rc;
+    uint8_t *d_comp = (uint8_t *)ctx->d_comp.p, *d_out = (uint8_t *)ctx->d_out.p;
+
+    /* queue every upload (chunk + 16-byte halo), one event each */
+    for (int k = 0; k < K; k++) {
+        const uint64_t a = (uint64_t)k * cbytes;
+        const uint64_t b = a + cbytes + 16 < nbytes ? a + cbytes + 16 : nbytes;
+        CK(cudaMemcpyAsync(d_comp + a, data + a, b - a, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (k == K - 1) CK(cudaMemsetAsync(d_comp + nbytes, 0, padded + 32 - nbytes, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * k], ctx->s_h2d));
+    }
+    CK(cudaEventRecord(ctx->pipe_t0, ctx->stream));
+    uint32_t cur = 0, launches = 0, tiles = 0;
+    uint64_t base = 0;
+    for (int k = 0; k < K; k++) {
+        const uint64_t a = (uint64_t)k * cbytes;
+        const bool last = k == K - 1;
+        const uint64_t own = last ? bits - 8 * a : 8 * cbytes;
+        const uint64_t avail = last ? own : 8 * (cbytes + 16);
+        const uint64_t readable = last ? padded + 32 - a : cbytes + 16;
+        uint64_t *h = ctx->h_pipe + 36 * (size_t)k;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * k], 0));
+        if ((rc = hb_shard_map(ctx, cb, d_comp + a, readable, own, avail, nullptr))) return rc;
+        CK(cudaMemcpyAsync(h, ctx->misc.p, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const uint64_t m = h[cur];
+        uint64_t n = m >> 8;
+        if (last && n && own + (m & 31u) > avail) n--;   /* cut-off last codeword emits nothing */
+        if (base + n > out_capacity) return HB_ERR_OUTPUT_FULL;
+        h[32] = cur; h[33] = base; h[34] = 0; h[35] = 0;
+        uint64_t *d_eb = (uint64_t *)ctx->d_eb.p + 4 * (size_t)k;
+        CK(cudaMemcpyAsync(d_eb, h + 32, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = hb_shard_emit(ctx, cb, d_comp + a, readable, own, avail, d_eb, d_out + base,
+                                out_capacity - base, nullptr))) return rc;
+        CK(cudaEventRecord(ctx->pipe_ev[2 * k + 1], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * k + 1], 0));
+        if (n) CK(cudaMemcpyAsync(out + base, d_out + base, n, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        launches += 6;
+        tiles += ctx->map_ntiles;
+        base += n;
+        cur = (uint32_t)(m & 31u);
+    }
+    CK(cudaEventRecord(ctx->pipe_t1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    memset(res, 0, sizeof(*res));
+    res->n_symbols = base;
+    res->exit_offset = cur;
+    res->launches = launches;
+    res->tiles = tiles;
+    float ms = 0;
+    /* first map to last emit on the compute stream (includes waits for uploads) */
+    if (cudaEventElapsedTime(&ms, ctx->pipe_t0, ctx->pipe_t1) == cudaSuccess) res->ms_total = ms;
+    /* output-full raised inside a kernel */
+    CK(cudaMemcpy(ctx->h_res, misc_words(ctx) + 36, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if ((uint32_t)ctx->h_res[0] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
+    return HB_OK;
+}
+
 extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
                               const uint8_t *data, uint64_t bits, uint8_t *out,
                               uint64_t out_capacity, hb_result *res) {
@@ -556,6 +684,8 @@ extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
     hb_codebook *cb = ctx->host_cb;
     const uint64_t nbytes = (bits + 7) / 8;
     const uint64_t padded = (nbytes + 15) & ~15ull;
+    if (nbytes >= 2 * ctx->pipe_chunk_bytes)
+        return decode_host_pipelined(ctx, cb, data, bits, out, out_capacity, res);
     do {
         if ((rc = ensure(ctx, ctx->d_comp, padded + 16))) break;
         if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) break;

@@ -80,6 +80,10 @@ const char *hb_last_error(const hb_ctx *ctx);
  * ctas_per_sm: persistent CTAs per SM (0 = occupancy-derived). */
 int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
 int  hb_ctx_sync(hb_ctx *ctx);
+/* hb_decode_host cuts streams of at least two chunks into chunks of this many
+ * compressed bytes (rounded to whole tiles) and overlaps upload, decode and
+ * download; 0 restores the default (32 MiB). */
+int  hb_ctx_set_host_chunk(hb_ctx *ctx, uint64_t bytes);
 /* Phase timing over many steps without host synchronisation in between:
  * _begin arms a ring of max_steps CUDA-event sets (one per following
  * hb_shard_map + hb_shard_emit pair); _collect synchronises the stream and

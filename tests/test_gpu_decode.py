@@ -69,6 +69,32 @@ def test_corpora_host_buffers(ctx, name):
         assert bytes(out[: f.usize]) == open(pt, "rb").read()
 
 
+@pytest.mark.parametrize("name,chunk", [("kjv", 64 << 10), ("kjv", 1 << 20), ("ecoli", 200000),
+                                        ("world192", 8192), ("paper1", 8192)])
+def test_host_path_pipelined_chunks(dev, name, chunk):
+    """hb_decode_host on streams longer than two chunks: byte-range chunks on one
+    GPU with overlapped upload / decode / download, pinned and pageable buffers."""
+    f = _stream(name)
+    c = hb.Context(0)
+    c.set_host_chunk(chunk)
+    for pinned in (False, True):
+        if pinned:
+            hc = torch.zeros(f.data.size, dtype=torch.uint8).pin_memory()
+            hc.copy_(torch.from_numpy(f.data))
+            ho = torch.zeros(f.usize + 16, dtype=torch.uint8).pin_memory()
+            data, out = hc.numpy(), ho.numpy()
+        else:
+            data, out = f.data, np.zeros(f.usize + 16, dtype=np.uint8)
+        res = hb.decode_host(c, f.tree, data, f.bits, out[: f.usize])
+        assert res["n_symbols"] == f.usize
+        assert O.sha256(out[: f.usize]) == O.CORPORA[name][2]
+        assert not out[f.usize:].any()
+    with pytest.raises(hb.HuffError) as e:
+        hb.decode_host(c, f.tree, f.data, f.bits, np.zeros(f.usize - 1, dtype=np.uint8))
+    assert e.value.code == -6
+    c.close()
+
+
 @pytest.mark.parametrize("name", ["hello", "paper1", "news", "book2", "kjv"])
 def test_approach_drop_in(name):
     """The bigtable suite (framework/mainrun.c:541-588) calling convention:
