@@ -311,7 +311,12 @@ HB_HD uint32_t hb_emit_fast(const hb_tables &tb, const uint32_t (&w)[WPT + 1], u
                 ent = hb_fast_load(tb, lo2, hi2, acc);
                 const uint32_t n = acc >> 8;
                 hb_st8(out, n, ent);
-                if (j < WPT - 1) { if (ent & (2u << 24)) hb_st8(out, n + 1, ent >> 8); }
+                /* words before the last: store the second byte unconditionally -- when the
+                 * probe held one symbol it is overwritten by the next probe's first store,
+                 * which always exists and is this thread's own symbol n + 1 (a probe in
+                 * word j < WPT-1 ends at most 63 bits in, i.e. inside word j+1).  Last
+                 * word: only a second symbol this thread owns. */
+                if (j < WPT - 1) hb_st8(out, n + 1, ent >> 8);
                 else { if ((ent & (2u << 24)) && n + 1 < c) hb_st8(out, n + 1, ent >> 8); }
                 acc = hb_acc_add(acc, ent);
             } while (!(acc & 0xE0u));
