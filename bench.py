@@ -321,9 +321,18 @@ def main():
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
     dom_name = {"sync": "hb_sync_kernel", "emit": "hb_emit_kernel"}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this
+    # same command (profiles/r01_traffic.json); only quoted for the configuration it was taken on
+    traffic = None
+    try:
+        if args.workload == "english1g" and (args.wpt or 8) == 8:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f)["kernels"][dom_name]["dram_bytes"]
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": b_alg,
         "kernel_ms": {"hb_sync_kernel": k_ms["sync"], "hb_scan_*": k_ms["scan"], "hb_emit_kernel": k_ms["emit"]},
         "decode_achieved": b_alg / (k_ms["total"] * 1e-3) / 1e9,
