@@ -497,21 +497,28 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             uint32_t hi_b = s_warp[15];
             if (hi_b > nvalid) hi_b = nvalid;
             if (lo_b < hi_b) {
-                /* staging -> global: s_out[al + (b - wb)] -> out[B + b], 16-byte vectors
-                 * aligned in both spaces, partial first/last vectors byte-wise */
+                /* staging -> global: s_out[al + (b - wb)] -> out[B + b].  The staging index
+                 * is congruent to the global address mod 16, so the 16-byte-aligned middle
+                 * goes out as ONE bulk asynchronous copy (TMA, cp.async.bulk) issued by a
+                 * single thread; the partial first / last vectors are stored byte-wise. */
                 uint8_t *gbase = out + B + wb - al;          /* 16-byte aligned */
                 const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
-                const uint32_t v0 = begb >> 4, nvec = (endb + 15u) >> 4;
-                for (uint32_t v = v0 + t; v < nvec; v += T) {
-                    const uint32_t b0 = v << 4;
-                    if (b0 >= begb && b0 + 16u <= endb) {
-                        *reinterpret_cast<uint4 *>(gbase + b0) =
-                            *reinterpret_cast<const uint4 *>(s_out + b0);
-                    } else {
-                        const uint32_t lo = b0 < begb ? begb : b0;
-                        const uint32_t hi = b0 + 16u < endb ? b0 + 16u : endb;
-                        for (uint32_t i = lo; i < hi; i++) gbase[i] = s_out[i];
+                const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
+                if (a0 < a1) {
+                    if (t == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(gbase + a0), "r"(s_out_saddr + a0), "r"(a1 - a0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (t >= 32 && t < 64) {                 /* head and tail bytes, one warp */
+                        const uint32_t i = t - 32;
+                        if (begb + i < a0) gbase[begb + i] = s_out[begb + i];
+                        if (a1 + i < endb) gbase[a1 + i] = s_out[a1 + i];
+                    }
+                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                } else {
+                    for (uint32_t i = begb + t; i < endb; i += T) gbase[i] = s_out[i];   /* < 32 bytes */
                 }
             }
             lo_b = hi_b > lo_b ? hi_b : lo_b;
