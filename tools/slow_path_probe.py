@@ -1,0 +1,97 @@
+"""Throughput on codes that synchronise badly (documented slow paths):
+ * "even": lengths {2,2,2,4,4,4,4} -- all even, odd entry offsets never merge
+ * "7or8": 64 codes of 7 bits + 128 codes of 8 bits -- almost fixed length
+ * "english": the bench model, for scale
+Builds the stream on the CPU (small), decodes on the GPU, checks bytes."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as O                  # noqa: E402
+import huffmandecoderongpus_b200 as hb  # noqa: E402
+
+
+def tree_from_lengths(lengths):
+    """canonical-ish complete prefix tree for the given code lengths (Kraft sum 1)"""
+    syms = sorted(range(len(lengths)), key=lambda s: (lengths[s], s))
+    nodes = [[0, -1, -1]]
+    codes = {}
+    code, prev = 0, 0
+    for s in syms:
+        code <<= (lengths[s] - prev)
+        prev = lengths[s]
+        v = 0
+        for i in range(lengths[s] - 1, -1, -1):
+            b = (code >> i) & 1
+            nxt = nodes[v][1 + b]
+            if nxt == -1:
+                nodes.append([0, -1, -1])
+                nxt = len(nodes) - 1
+                nodes[v][1 + b] = nxt
+            v = nxt
+        nodes[v][0] = s
+        codes[s] = [(code >> i) & 1 for i in range(lengths[s] - 1, -1, -1)]
+        code += 1
+    t = np.zeros(len(nodes), dtype=hb.NODE_DTYPE)
+    for i, (sym, a, b) in enumerate(nodes):
+        t[i] = (sym, a, b)
+    return t, codes
+
+
+def encode(codes, syms):
+    lens = np.array([len(codes[s]) for s in range(len(codes))])
+    total = int(lens[syms].sum())
+    bits = np.zeros(total + 64, dtype=np.uint8)
+    pos = np.concatenate([[0], np.cumsum(lens[syms])[:-1]])
+    maxl = int(lens.max())
+    table = np.zeros((len(codes), maxl), dtype=np.uint8)
+    for s, c in codes.items():
+        table[s, : len(c)] = c
+    for k in range(maxl):
+        m = lens[syms] > k
+        bits[pos[m] + k] = table[syms[m], k]
+    data = np.packbits(bits, bitorder="little")
+    return np.concatenate([data, np.zeros(32, np.uint8)]), total
+
+
+def run(name, tree, data, bits, syms, ctx, dev):
+    cb = hb.Codebook(ctx, tree)
+    nb = (bits + 7) // 8
+    comp = torch.zeros((nb + 15) // 16 * 16 + 32, dtype=torch.uint8, device=dev)
+    comp[:nb] = torch.from_numpy(data[:nb]).to(dev)
+    out = torch.zeros(syms.size + 64, dtype=torch.uint8, device=dev)
+    best = None
+    for _ in range(4):
+        res = hb.decode_device(ctx, cb, comp.data_ptr(), comp.numel(), bits, out.data_ptr(), syms.size)
+        best = res["ms_total"] if best is None else min(best, res["ms_total"])
+    ok = res["n_symbols"] == syms.size and np.array_equal(out[: syms.size].cpu().numpy(), syms)
+    print(f"{name:>8}: maxlen {cb.maxlen} minlen {cb.minlen}, {syms.size} symbols, {nb} B in: "
+          f"{best:.3f} ms = {syms.size / best / 1e6:.1f} GB/s out, sync {res['ms_sync']:.3f} emit {res['ms_emit']:.3f}  {'OK' if ok else 'MISMATCH'}")
+
+
+def main():
+    dev = torch.device("cuda:0")
+    ctx = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(1)
+    n = 1 << 24
+    for name, lengths in (("even", [2, 2, 2, 4, 4, 4, 4]), ("7or8", [7] * 64 + [8] * 128)):
+        p = np.array([2.0 ** -l for l in lengths])
+        syms = rng.choice(len(lengths), size=n, p=p / p.sum()).astype(np.uint8)
+        tree, codes = tree_from_lengths(lengths)
+        data, bits = encode(codes, syms)
+        st = O.Stream(tree, data, bits, n)
+        assert np.array_equal(O.simple_decode(st, bits=min(bits, 1 << 20))[:1000], syms[:1000])
+        run(name, tree, data, bits, syms, ctx, dev)
+    m = hb.Model(hb.MODEL_ENGLISH)
+    f, syms = m.huff_file_cpu(7, n)
+    run("english", f.tree, f.data, f.bits, syms, ctx, dev)
+
+
+if __name__ == "__main__":
+    main()
