@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--workload", default="english1g", choices=list(WORKLOADS))
     ap.add_argument("--wpt", type=int, default=0, help="words per thread (0 = library default)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--sync-path", default="auto", choices=["auto", "probe"],
+                    help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -233,6 +235,7 @@ def main():
     n_total = n_per * world
     ctx = hb.Context(local, stream=torch.cuda.current_stream().cuda_stream,
                      words_per_thread=args.wpt, ctas_per_sm=args.ctas_per_sm)
+    ctx.set_sync_path(args.sync_path)
     model = hb.Model(kind)
     cb = hb.Codebook(ctx, model.tree)
 
@@ -279,6 +282,7 @@ def main():
     # ---- correctness of this very configuration (untimed) -------------------------
     res = step(want_result=True)
     n_mine = res["n_symbols"]
+    launches_per_step = res["launches"] + (1 if world > 1 else 0)   # + hb_compose_kernel
     bad = hb.gen_verify_device(ctx, model, SEED, res["out_base"], n_mine, out.data_ptr())
     tot = torch.tensor([n_mine, bad], dtype=torch.int64, device=dev)
     if world > 1:
@@ -319,14 +323,15 @@ def main():
     b_alg = comp_bytes_own + n_mine                 # compressed read once + decoded written once
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
-    dom_name = {"sync": "hb_sync_kernel", "emit": "hb_emit_kernel"}[dom]
+    sync_name = "hb_fsm_sync_kernel" if args.sync_path == "auto" else "hb_sync_kernel"
+    dom_name = {"sync": sync_name, "emit": "hb_emit_kernel"}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this
     # same command (profiles/r01_traffic.json); only quoted for the configuration it was taken on
     traffic = None
     try:
         if args.workload == "english1g" and (args.wpt or 8) == 8:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 traffic = json.load(f)["kernels"][dom_name]["dram_bytes"]
     except Exception:
         traffic = None
@@ -334,7 +339,7 @@ def main():
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": b_alg,
-        "kernel_ms": {"hb_sync_kernel": k_ms["sync"], "hb_scan_*": k_ms["scan"], "hb_emit_kernel": k_ms["emit"]},
+        "kernel_ms": {sync_name: k_ms["sync"], "hb_scan_*+hb_fix": k_ms["scan"], "hb_emit_kernel": k_ms["emit"]},
         "decode_achieved": b_alg / (k_ms["total"] * 1e-3) / 1e9,
         "decode_frac": b_alg / (k_ms["total"] * 1e-3) / 1e9 / peak,
         "kernel_share_of_step": k_ms[dom] / k_ms["total"],
@@ -400,12 +405,12 @@ def main():
             "config": {"workload": args.workload, "description": desc, "seed": SEED,
                        "symbols_total": n_total, "compressed_bytes_total": int(nbytes_total),
                        "bits_total": int(bits_total), "max_code_length": model.maxlen,
-                       "words_per_thread": args.wpt or 8,
+                       "words_per_thread": args.wpt or 8, "sync_path": args.sync_path,
                        "parallelism": f"byte-range shards x{world}, 1 NCCL all-gather of 32-entry maps" if world > 1 else "single GPU",
                        "l2": "inputs and outputs larger than L2 (no flush needed)",
                        "compressed_input_GB_per_s": in_gbs},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 6 * args.steps + (args.steps if world > 1 else 0),
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -62,7 +62,9 @@ class LutC(C.Structure):
                 ("w1", C.c_uint32), ("maxlen", C.c_uint32), ("minlen", C.c_uint32),
                 ("n_leaves", C.c_uint32), ("wf", C.c_uint32),
                 ("stab", C.POINTER(C.c_uint32)), ("etab", C.POINTER(C.c_uint32)),
-                ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256)]
+                ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256),
+                ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
+                ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256)]
 
 
 class RefCompressedData(C.Structure):
@@ -100,6 +102,7 @@ def lib():
     L.hb_ctx_destroy.argtypes = [vp]
     L.hb_ctx_destroy.restype = None
     L.hb_ctx_configure.argtypes = [vp, i32, i32]
+    L.hb_ctx_set_sync_path.argtypes = [vp, i32]
     L.hb_ctx_sync.argtypes = [vp]
     L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
     L.hb_ctx_timing_begin.argtypes = [vp, i32]
@@ -195,7 +198,14 @@ def build_lut(tree, w1_max=0, w2_max=0):
     _check(lib().hb_lut_build(tree.ctypes.data, int(tree.shape[0]), w1_max, w2_max, C.byref(lut)),
            "hb_lut_build")
     try:
+        ns = int(lut.fsm_states)
         return {
+            "fsm_states": ns,
+            "fsm": (np.ctypeslib.as_array(lut.fsm, shape=(ns * 256,)).copy() if ns
+                    else np.zeros(1, np.uint16)),
+            "fsm_bstep": (np.ctypeslib.as_array(lut.fsm_bstep, shape=(ns * 2,)).copy() if ns
+                          else np.zeros(2, np.uint16)),
+            "fsm_depth": np.array(lut.fsm_depth, dtype=np.uint8),
             "entries": np.ctypeslib.as_array(lut.entries, shape=(lut.n_entries,)).copy(),
             "w1": lut.w1, "maxlen": lut.maxlen, "minlen": lut.minlen, "n_leaves": lut.n_leaves,
             "wf": lut.wf,
@@ -254,6 +264,10 @@ class Context:
 
     def configure(self, words_per_thread=0, ctas_per_sm=0):
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
+
+    def set_sync_path(self, path):
+        """"auto" (transducer sync kernel on full tiles when the code has one) or "probe"."""
+        _check(lib().hb_ctx_set_sync_path(self.h, {"auto": 0, "probe": 1}[path]), "hb_ctx_set_sync_path")
 
     def set_host_chunk(self, nbytes):
         _check(lib().hb_ctx_set_host_chunk(self.h, nbytes), "hb_ctx_set_host_chunk")

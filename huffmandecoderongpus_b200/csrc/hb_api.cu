@@ -18,6 +18,7 @@ struct hb_codebook {
     hb_ctx *ctx;
     hb_lut lut;        /* host copy (entries kept for the encoder / tests) */
     uint32_t *d_lut;
+    uint8_t *d_fsm;    /* [fsm u16 x states*256][depth u8 x 256][bstep u16 x states*2], or NULL */
     double implied_avg_len;   /* sum over leaves of 2^-len * len */
 };
 
@@ -33,6 +34,8 @@ struct hb_ctx {
     cudaDeviceProp prop;
     int wpt = 8;
     int ctas_per_sm = 0;
+    int sync_path = HB_SYNC_AUTO;
+    uint32_t last_launches = 0;   /* kernels launched by the last map + emit pair */
     cudaEvent_t ev0[HB_NEV];   /* default event set */
     cudaEvent_t *ev = nullptr; /* set used by the current step */
     cudaEvent_t *tim_ev = nullptr; /* optional ring: tim_cap steps x HB_NEV events */
@@ -174,6 +177,12 @@ extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_
     return HB_OK;
 }
 
+extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
+    if (!ctx || (path != HB_SYNC_AUTO && path != HB_SYNC_PROBE)) return HB_ERR_ARG;
+    ctx->sync_path = path;
+    return HB_OK;
+}
+
 extern "C" int hb_ctx_set_host_chunk(hb_ctx *ctx, uint64_t bytes) {
     if (!ctx) return HB_ERR_ARG;
     ctx->pipe_chunk_bytes = bytes ? bytes : (32ull << 20);
@@ -207,6 +216,7 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
     if (!cb) return HB_ERR_NOMEM;
     cb->ctx = ctx;
     cb->d_lut = nullptr;
+    cb->d_fsm = nullptr;
     int rc = hb_lut_build(tree, nodes, 0, 0, &cb->lut);
     if (rc != HB_OK) { delete cb; return rc; }
     {   /* expected code length under the code's own implied distribution */
@@ -238,9 +248,20 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         e = cudaMemcpyAsync(cb->d_lut + n1, cb->lut.stab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(cb->d_lut + n1 + nf, cb->lut.etab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && cb->lut.fsm_states) {
+        const size_t ns = cb->lut.fsm_states;
+        e = cudaMalloc((void **)&cb->d_fsm, ns * 512 + 256 + ns * 4);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(cb->d_fsm, cb->lut.fsm, ns * 512, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(cb->d_fsm + ns * 512, cb->lut.fsm_depth, 256, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(cb->d_fsm + ns * 512 + 256, cb->lut.fsm_bstep, ns * 4, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (cb->d_lut) cudaFree(cb->d_lut);
+        if (cb->d_fsm) cudaFree(cb->d_fsm);
         hb_lut_free(&cb->lut);
         delete cb;
         return cuda_fail(ctx, e, "codebook upload");
@@ -253,6 +274,7 @@ extern "C" void hb_codebook_destroy(hb_codebook *cb) {
     if (!cb) return;
     cudaSetDevice(cb->ctx->device);
     if (cb->d_lut) cudaFree(cb->d_lut);
+    if (cb->d_fsm) cudaFree(cb->d_fsm);
     hb_lut_free(&cb->lut);
     delete cb;
 }
@@ -298,11 +320,11 @@ static void stage_geometry(const hb_codebook *cb, int wpt, uint32_t *win, uint32
 }
 
 template <typename K>
-static int grid_for(hb_ctx *ctx, K kernel, size_t smem, uint32_t ntiles, int *grid) {
+static int grid_for(hb_ctx *ctx, K kernel, size_t smem, uint32_t ntiles, int *grid, int threads = HB_T) {
     /* static (16 KB fast table) + dynamic can exceed the 48 KB default: always opt in */
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, HB_T, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) {
         snprintf(ctx->err, sizeof(ctx->err), "kernel does not fit an SM (smem %zu)", smem);
         return HB_ERR_CUDA;
@@ -341,8 +363,63 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
 
 static uint64_t *misc_words(hb_ctx *ctx) { return (uint64_t *)ctx->misc.p; }
 
+/* Transducer sync kernel over tiles [0, n_full).  G groups of HB_T threads share one
+ * table copy per CTA; G is chosen for the most resident warps per SM. */
+template <int WPT, int G>
+static int try_fsm_geometry(hb_ctx *ctx, size_t table_bytes, int *occ, size_t *smem) {
+    *smem = table_bytes + (size_t)G * hb_fsm_group_words<WPT>() * sizeof(uint32_t);
+    *occ = 0;
+    if (*smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return HB_OK;
+    CK(cudaFuncSetAttribute(hb_fsm_sync_kernel<WPT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hb_fsm_sync_kernel<WPT, G>, G * HB_T, *smem));
+    return HB_OK;
+}
+
+template <int WPT, int G>
+static int run_fsm_sync(hb_ctx *ctx, const hb_stream_args &a, const hb_fsm_args &fa, uint32_t n_full,
+                        int occ, size_t smem) {
+    if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < occ) occ = ctx->ctas_per_sm;
+    uint64_t grid = (uint64_t)occ * (uint64_t)ctx->prop.multiProcessorCount;
+    const uint64_t need = ((uint64_t)n_full + G - 1) / G;
+    if (grid > need) grid = need;
+    hb_fsm_sync_kernel<WPT, G><<<(int)grid, G * HB_T, smem, ctx->stream>>>(
+        a, fa, n_full, (uint16_t *)ctx->subs.p, (uint32_t *)ctx->tmaps.p);
+    CK(cudaGetLastError());
+    ctx->last_launches++;
+    return HB_OK;
+}
+
 template <int WPT>
-static int launch_map(hb_ctx *ctx, const hb_stream_args &a, uint64_t *d_map) {
+static int launch_fsm_sync(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a, uint32_t n_full) {
+    const size_t ns = cb->lut.fsm_states;
+    hb_fsm_args fa;
+    fa.tab = (const uint16_t *)cb->d_fsm;
+    fa.depth = cb->d_fsm + ns * 512;
+    fa.bstep = (const uint16_t *)(cb->d_fsm + ns * 512 + 256);
+    fa.nstates = (uint32_t)ns;
+    const size_t table_bytes = ns * 512 + 256;
+    int occ[3] = {0, 0, 0}, rc;
+    size_t smem[3] = {0, 0, 0};
+    if ((rc = try_fsm_geometry<WPT, 1>(ctx, table_bytes, &occ[0], &smem[0]))) return rc;
+    if ((rc = try_fsm_geometry<WPT, 2>(ctx, table_bytes, &occ[1], &smem[1]))) return rc;
+    if ((rc = try_fsm_geometry<WPT, 4>(ctx, table_bytes, &occ[2], &smem[2]))) return rc;
+    /* most resident warps; on a tie the larger group count (fewer table copies) */
+    int best = -1, best_warps = 0;
+    for (int i = 0; i < 3; i++) {
+        const int warps = occ[i] * (1 << i) * (HB_T / 32);
+        if (warps >= best_warps && warps > 0) { best = i; best_warps = warps; }
+    }
+    switch (best) {
+    case 0: return run_fsm_sync<WPT, 1>(ctx, a, fa, n_full, occ[0], smem[0]);
+    case 1: return run_fsm_sync<WPT, 2>(ctx, a, fa, n_full, occ[1], smem[1]);
+    case 2: return run_fsm_sync<WPT, 4>(ctx, a, fa, n_full, occ[2], smem[2]);
+    }
+    snprintf(ctx->err, sizeof(ctx->err), "transducer table (%zu B) does not fit an SM", table_bytes);
+    return HB_ERR_CUDA;
+}
+
+template <int WPT>
+static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a, uint64_t *d_map) {
     const uint32_t ncta = (a.ntiles + 1023u) / 1024u;
     int rc;
     if ((rc = ensure(ctx, ctx->subs, sizeof(uint16_t) * (size_t)a.ntiles * HB_T))) return rc;
@@ -354,12 +431,23 @@ static int launch_map(hb_ctx *ctx, const hb_stream_args &a, uint64_t *d_map) {
     if ((rc = ensure(ctx, ctx->tile_base, sizeof(uint64_t) * (size_t)a.ntiles))) return rc;
 
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    size_t smem = sync_smem_bytes<WPT>(a.wf);
-    int grid = 1;
-    if ((rc = grid_for(ctx, hb_sync_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
-    hb_sync_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(a, (uint16_t *)ctx->subs.p,
-                                                           (uint32_t *)ctx->tmaps.p);
-    CK(cudaGetLastError());
+    ctx->last_launches = 0;
+    uint32_t tile0 = 0;
+    if (ctx->sync_path == HB_SYNC_AUTO && cb->d_fsm && a.minlen != a.maxlen) {
+        /* full tiles: byte-step transducer kernel */
+        const uint32_t n_full = (uint32_t)(a.bits_own / ((uint64_t)HB_T * 32u * WPT));
+        if (n_full && (rc = launch_fsm_sync<WPT>(ctx, cb, a, n_full))) return rc;
+        tile0 = n_full;
+    }
+    if (tile0 < a.ntiles) {
+        size_t smem = sync_smem_bytes<WPT>(a.wf);
+        int grid = 1;
+        if ((rc = grid_for(ctx, hb_sync_kernel<WPT>, smem, a.ntiles - tile0, &grid))) return rc;
+        hb_sync_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(a, tile0, (uint16_t *)ctx->subs.p,
+                                                               (uint32_t *)ctx->tmaps.p);
+        CK(cudaGetLastError());
+        ctx->last_launches++;
+    }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     hb_scan_up_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>((const uint32_t *)ctx->tmaps.p, a.ntiles,
                                                           (uint64_t *)ctx->wmaps.p,
@@ -368,6 +456,7 @@ static int launch_map(hb_ctx *ctx, const hb_stream_args &a, uint64_t *d_map) {
     hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
                                                   (uint64_t *)ctx->cprefix.p, misc_words(ctx));
     CK(cudaGetLastError());
+    ctx->last_launches += 2;
     if (d_map)
         CK(cudaMemcpyAsync(d_map, misc_words(ctx), 32 * sizeof(uint64_t), cudaMemcpyDeviceToDevice,
                            ctx->stream));
@@ -452,9 +541,9 @@ extern "C" int hb_shard_map(hb_ctx *ctx, const hb_codebook *cb, const void *d_co
         return HB_OK;
     }
     switch (ctx->wpt) {
-    case 4: return launch_map<4>(ctx, a, d_map);
-    case 8: return launch_map<8>(ctx, a, d_map);
-    case 16: return launch_map<16>(ctx, a, d_map);
+    case 4: return launch_map<4>(ctx, cb, a, d_map);
+    case 8: return launch_map<8>(ctx, cb, a, d_map);
+    case 16: return launch_map<16>(ctx, cb, a, d_map);
     }
     return HB_ERR_ARG;
 }
@@ -529,7 +618,7 @@ extern "C" int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_c
     default: rc = HB_ERR_ARG;
     }
     if (rc) return rc;
-    launches = 6;
+    launches = ctx->last_launches + 3;   /* + scan down, fix, emit */
     if (res) return finish_result(ctx, a.ntiles, launches, res);
     return HB_OK;
 }
@@ -629,7 +718,7 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
         CK(cudaEventRecord(ctx->pipe_ev[2 * k + 1], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * k + 1], 0));
         if (n) CK(cudaMemcpyAsync(out + base, d_out + base, n, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        launches += 6;
+        launches += ctx->last_launches + 3;
         tiles += ctx->map_ntiles;
         base += n;
         cur = (uint32_t)(m & 31u);

@@ -414,4 +414,134 @@ HB_HD void hb_fix_entries(const hb_tables &tb, const WordFn &word, uint16_t *sub
     }
 }
 
+/* ==== byte-step transducer walks (sync kernel fast path, full tiles) ==========
+ * Table layout in hb_format.h.  A chain is followed 8 bits at a time; its state at
+ * a byte boundary is the internal tree node of the unfinished codeword (0 = a
+ * codeword starts exactly there), so two chains are identical from a boundary on
+ * iff their states there are equal -- an exact merge test with no position
+ * arithmetic, no data-dependent trip count and no divergence.  Per 32-bit word the
+ * walk records  rec = (state after the word) << 8 | (codewords ENDING in the word).
+ *
+ * The rest of the pipeline (tile maps, scan, fix, emit) speaks "first codeword START
+ * at or after a boundary" and "codewords STARTING in a run".  With d = depth(state)
+ * at a boundary b, the unfinished codeword began at b - d, so
+ *     forward offset   = length(codeword at b - d) - d          (hb_fsm_fwd)
+ *     starts in a run  = ends in it - [d_in > 0] + [d_out > 0].                  */
+
+struct hb_fsm {
+    const uint16_t *tab;     /* fsm[state * 256 + byte] (host emulation) */
+    uint32_t tab_saddr;      /* its shared-state-space address (device) */
+    const uint8_t *depth;    /* fsm_depth[state] */
+    const uint16_t *bstep;   /* fsm_bstep[2 * state + bit] */
+};
+
+/* entry for (state in bits 15:8 of ent, byte i of w) */
+template <int I>
+HB_HD uint32_t hb_fsm_step(const hb_fsm &f, uint32_t ent, uint32_t w) {
+#ifdef __CUDA_ARCH__
+    /* one PRMT: byte 0 <- byte I of w, byte 1 <- state, bytes 2..3 <- 0 (byte 3 of ent) */
+    const uint32_t t = __byte_perm(ent, w, 0x3314 + I);
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(f.tab_saddr + 2u * t));
+    return v;
+#else
+    return f.tab[(ent & 0xff00u) | ((w >> (8 * I)) & 0xffu)];
+#endif
+}
+
+/* one stream word: ent in = any value whose bits 15:8 hold the entering state (bits
+ * 31:16 zero), out = the last entry read.  Returns the word's record. */
+HB_HD uint32_t hb_fsm_word(const hb_fsm &f, uint32_t w, uint32_t &ent) {
+    ent = hb_fsm_step<0>(f, ent, w);
+    uint32_t acc = ent;
+    ent = hb_fsm_step<1>(f, ent, w); acc += ent;
+    ent = hb_fsm_step<2>(f, ent, w); acc += ent;
+    ent = hb_fsm_step<3>(f, ent, w); acc += ent;
+    return (ent & 0xff00u) | (acc & 0xffu);   /* at most 8 ends per byte: the low byte cannot carry */
+}
+
+HB_HD uint32_t hb_frec_state(uint32_t r) { return (r >> 8) & 0xffu; }
+HB_HD uint32_t hb_frec_ends(uint32_t r) { return r & 0xffu; }
+
+template <int WPT>
+HB_HD void hb_fsm_walk(const hb_fsm &f, const uint32_t (&w)[WPT + 1], uint32_t state,
+                       uint32_t (&rec)[WPT]) {
+    uint32_t ent = state << 8;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) rec[j] = hb_fsm_word(f, w[j], ent);
+}
+
+/* Re-walk from a new entering state until the chain meets the recorded one behind
+ * some word (identical from there on) or the subsequence ends; rec becomes the chain
+ * of `state`.  Returns true when the state behind the LAST word changed. */
+template <int WPT>
+HB_HD bool hb_fsm_rewalk(const hb_fsm &f, const uint32_t (&w)[WPT + 1], uint32_t state,
+                         uint32_t (&rec)[WPT]) {
+    uint32_t ent = state << 8;
+    bool merged = false;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        if (!merged) {
+            const uint32_t r = hb_fsm_word(f, w[j], ent);
+            merged = ((r ^ rec[j]) & 0xff00u) == 0u;
+            rec[j] = r;
+        }
+    }
+    return !merged;
+}
+
+/* forward offset of the first codeword start at or after a word boundary whose state
+ * has depth d: prev = the word before the boundary, next = the word after it */
+HB_HD uint32_t hb_fsm_fwd(const hb_lutref &slow, uint32_t prev, uint32_t next, uint32_t d) {
+    if (d == 0u) return 0u;
+    uint32_t sym;
+    return hb_probe(slow, prev, next, 32u - d, &sym) - d;
+}
+
+/* Chain of a non-zero tile entry offset e through a FULL tile (T * WPT words):
+ * bit steps to the next byte boundary, byte steps to the next word boundary, then
+ * word by word until its state equals the hypothesis-0 chain's recorded state (exit
+ * and remaining count are then those of hypothesis 0) or the tile ends.
+ * recs[j * T + t]: converged records of hypothesis 0; cs[t]: exclusive prefix over
+ * subsequences of its END counts, E0 their total; X0 / d0: its forward exit offset
+ * and exit depth.  Returns packed (starts << 8) | exit offset. */
+template <int WPT, int T, class WordFn>
+HB_HD uint32_t hb_fsm_hyp_walk(const hb_fsm &f, const hb_lutref &slow, const WordFn &word,
+                               const uint16_t *recs, const uint32_t *cs, uint32_t E0, uint32_t X0,
+                               uint32_t d0, uint32_t e) {
+    uint32_t pos = e, n = 0, st = 0;
+    const uint32_t w0 = word(0);
+    while (pos & 7u) {
+        const uint32_t r = f.bstep[2u * st + ((w0 >> pos) & 1u)];
+        n += r >> 8;
+        st = r & 0xffu;
+        pos++;
+    }
+    uint32_t ent = st << 8;
+    while (pos & 31u) {
+#ifdef __CUDA_ARCH__
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v)
+            : "r"(f.tab_saddr + 2u * ((ent & 0xff00u) | ((w0 >> pos) & 0xffu))));
+        ent = v;
+#else
+        ent = f.tab[(ent & 0xff00u) | ((w0 >> pos) & 0xffu)];
+#endif
+        n += ent & 0xffu;
+        pos += 8u;
+    }
+    for (uint32_t wi = 0;;) {           /* pos == 32 * (wi + 1): behind word wi */
+        const uint32_t t = wi / WPT, j = wi % WPT;
+        if ((((uint32_t)recs[j * T + t] ^ ent) & 0xff00u) == 0u) {
+            uint32_t upto = cs[t];      /* hypothesis-0 ends through word wi */
+            for (uint32_t jj = 0; jj <= j; jj++) upto += hb_frec_ends(recs[jj * T + t]);
+            return hb_map_pack32(X0, n + E0 - upto + (d0 ? 1u : 0u));
+        }
+        if (++wi == (uint32_t)(T * WPT)) break;
+        n += hb_frec_ends(hb_fsm_word(f, word(wi), ent));
+    }
+    const uint32_t d = f.depth[hb_frec_state(ent)];
+    return hb_map_pack32(hb_fsm_fwd(slow, word(T * WPT - 1), word(T * WPT), d), n + (d ? 1u : 0u));
+}
+
 #endif /* HB_CORE_CUH_ */

@@ -20,4 +20,14 @@
 #define HB_FAST_MARK 0xE0u
 #define HB_E_MAXSYM 2
 #define HB_WF_MAX 12               /* widest fast-table index (16 KB per table) */
+
+/* Byte-step transducer of the sync kernel's fast path (the GPU counterpart of the
+ * reference's jump table, framework/jumptableapproach.c:40-99, with jumpbits = 8 and
+ * no symbol output).  States are the internal nodes of the tree, root = state 0, at
+ * most HB_FSM_MAX_STATES of them (every tree over a byte alphabet qualifies).
+ *   fsm[s * 256 + b] (u16), b = the next 8 stream bits, bit 0 first:
+ *       [15:8] state after the 8 bits, [3:0] number of codewords that END inside them
+ *   fsm_depth[s]  = bits of the unfinished codeword already consumed in state s
+ *   fsm_bstep[2 * s + bit] (u16): [7:0] next state, bit 8 = this bit ended a codeword */
+#define HB_FSM_MAX_STATES 256
 #endif

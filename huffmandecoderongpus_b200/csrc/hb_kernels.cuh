@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t hb_block_exscan(uint32_t v, uint32_t *s_warp
 /* ------------------------------------------------------------------------- */
 template <int WPT>
 __global__ void __launch_bounds__(HB_T, HB_SYNC_MIN_CTAS)
-hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
+hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
@@ -136,7 +136,7 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
 
     const bool fixed_len = a.minlen == a.maxlen;
-    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0 + blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
         uint32_t w[WPT + 1];
@@ -205,6 +205,166 @@ hb_sync_kernel(hb_stream_args a, uint16_t *__restrict__ subs, uint32_t *__restri
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
         __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Sync kernel, fast path: FULL tiles of a code whose transducer fits shared memory
+ * (hb_format.h; every byte-alphabet tree).  Same outputs as hb_sync_kernel -- the
+ * (entry offset, starts) record of every subsequence and the tile's 32-entry map --
+ * but the chains are followed by the byte-step transducer: 4 instructions per 8
+ * stream bits (PRMT, LEA, LDS.U16, IADD), no data-dependent loop, no divergence.
+ * A CTA holds ONE copy of the table (up to 128 KB) and G independent groups of
+ * HB_T threads, each working on its own tile behind its own named barrier. */
+struct hb_fsm_args {
+    const uint16_t *tab;     /* nstates * 256 */
+    const uint16_t *bstep;   /* nstates * 2 */
+    const uint8_t *depth;    /* 256 */
+    uint32_t nstates;
+};
+
+__device__ __forceinline__ void hb_group_sync(uint32_t id) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(HB_T) : "memory");
+}
+__device__ __forceinline__ bool hb_group_or(uint32_t id, bool p) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred r, %1, %3, q;\n\t"
+                 "selp.u32 %0, 1, 0, r;\n\t}"
+                 : "=r"(r) : "r"(id), "r"((uint32_t)p), "n"(HB_T) : "memory");
+    return r != 0u;
+}
+
+/* exclusive scan over the HB_T threads of a group; s_warp: >= 9 words of the group */
+__device__ __forceinline__ uint32_t hb_group_exscan(uint32_t v, uint32_t *s_warp, uint32_t id,
+                                                    uint32_t tg, uint32_t *total) {
+    const uint32_t lane = tg & 31u, wid = tg >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+    }
+    if (lane == 31u) s_warp[wid] = inc;
+    hb_group_sync(id);
+    if (wid == 0u) {
+        uint32_t x = (lane < HB_T / 32) ? s_warp[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int d = 1; d < HB_T / 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= (uint32_t)d) xi += y;
+        }
+        if (lane < HB_T / 32) s_warp[lane] = xi - x;
+        if (lane == HB_T / 32 - 1) s_warp[HB_T / 32] = xi;
+    }
+    hb_group_sync(id);
+    *total = s_warp[HB_T / 32];
+    return s_warp[wid] + inc - v;
+}
+
+struct hb_global_words {
+    const uint32_t *words;
+    uint64_t base, nwords;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return base + i < nwords ? __ldg(words + base + i) : 0u;
+    }
+};
+
+/* per-group shared memory of hb_fsm_sync_kernel, in 32-bit words */
+template <int WPT>
+__host__ __device__ constexpr uint32_t hb_fsm_group_words() {
+    return (uint32_t)(WPT * HB_T / 2 + HB_T + HB_T + 16);
+}
+
+template <int WPT, int G>
+__global__ void __launch_bounds__(G * HB_T, (G == 1 ? 6 : (G == 2 ? 3 : 1)))
+hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
+                   uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem);                  /* nstates * 256 */
+    uint8_t *s_depth = reinterpret_cast<uint8_t *>(smem + fa.nstates * 128u);   /* 256 */
+    const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
+    uint32_t *s_grp = smem + fa.nstates * 128u + 64u + g * hb_fsm_group_words<WPT>();
+    uint16_t *s_rec = reinterpret_cast<uint16_t *>(s_grp);                 /* WPT * T records */
+    uint32_t *s_cs = s_grp + WPT * T / 2;                                  /* T: prefix of END counts */
+    uint32_t *s_exit = s_cs + T;                                           /* T: state behind each subsequence */
+    uint32_t *s_warp = s_exit + T;                                         /* 16; [12..15]: X0, exit depth */
+
+    {   /* table: 16-byte copies by the whole CTA */
+        const uint4 *src = reinterpret_cast<const uint4 *>(fa.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+        for (uint32_t i = threadIdx.x; i < fa.nstates * 32u; i += G * T) dst[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < 256u; i += G * T) s_depth[i] = __ldg(fa.depth + i);
+    }
+    __syncthreads();
+    hb_fsm f;
+    f.tab = s_tab;
+    f.tab_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_tab));
+    f.depth = s_depth;
+    f.bstep = fa.bstep;
+    const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
+
+    for (uint32_t tile = blockIdx.x * G + g; tile < ntiles_full; tile += gridDim.x * G) {
+        const uint64_t wbase = (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT;
+        uint32_t w[WPT + 1];
+        hb_load_words<WPT>(a, wbase, w);
+
+        /* chain of the guess "a codeword starts at bit 0 of my subsequence" */
+        uint32_t rec[WPT];
+        uint32_t st_in = 0u;
+        hb_fsm_walk<WPT>(f, w, st_in, rec);
+        s_exit[t] = hb_frec_state(rec[WPT - 1]);
+        hb_group_sync(bar);
+
+        /* stitch: my entering state is my left neighbour's exit state; repeat until no
+         * exit state moves */
+        for (;;) {
+            bool changed = false;
+            if (t > 0) {
+                const uint32_t sn = s_exit[t - 1];
+                if (sn != st_in) {
+                    st_in = sn;
+                    changed = hb_fsm_rewalk<WPT>(f, w, st_in, rec);
+                }
+            }
+            if (!hb_group_or(bar, changed)) break;
+            s_exit[t] = hb_frec_state(rec[WPT - 1]);
+            hb_group_sync(bar);
+        }
+
+        /* records in the pipeline's convention: forward entry offset, codeword STARTS */
+        uint32_t ends = 0;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            ends += hb_frec_ends(rec[j]);
+            s_rec[j * T + t] = (uint16_t)rec[j];
+        }
+        const uint32_t d_in = s_depth[st_in], d_out = s_depth[hb_frec_state(rec[WPT - 1])];
+        uint32_t e = 0u;
+        if (d_in) e = hb_fsm_fwd(slow, __ldg(a.words + wbase - 1), w[0], d_in);   /* t > 0 here */
+        subs[(uint64_t)tile * T + t] = hb_sub_pack(e, ends - (d_in ? 1u : 0u) + (d_out ? 1u : 0u));
+        if (t == T - 1) {
+            s_warp[12] = hb_fsm_fwd(slow, w[WPT - 1], w[WPT], d_out);
+            s_warp[13] = d_out;
+        }
+        uint32_t E0;
+        s_cs[t] = hb_group_exscan(ends, s_warp, bar, t, &E0);
+        hb_group_sync(bar);
+
+        /* tile map: hypothesis 0 is the converged chain; 1..maxlen-1 are followed by
+         * one lane each until they meet it */
+        if (t < 32) {
+            const uint32_t X0 = s_warp[12], d0 = s_warp[13];
+            uint32_t m = hb_map_pack32(X0, E0 + (d0 ? 1u : 0u));
+            if (t > 0 && t < a.maxlen) {
+                hb_global_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
+                m = hb_fsm_hyp_walk<WPT, T>(f, slow, word, s_rec, s_cs, E0, X0, d0, t);
+            }
+            tmaps[(uint64_t)tile * 32 + t] = m;
+        }
+        hb_group_sync(bar);
     }
 }
 

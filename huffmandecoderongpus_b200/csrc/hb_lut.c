@@ -31,6 +31,7 @@ typedef struct builder {
 
 static int is_leaf(const hb_node *n) { return n->izero == -1 && n->ione == -1; }
 static int build_fast_tables(const hb_node *tree, hb_lut *out);
+static int build_fsm(const hb_node *tree, int nodes, hb_lut *out);
 
 /* iterative validation: every reachable node is a full internal node or a leaf,
  * indices in range, no node reached twice (=> a tree, no cycles), depth <= 32 */
@@ -185,6 +186,62 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
     collect_codes(tree, 0, 0, 0, out, have);
     int frc = build_fast_tables(tree, out);
     if (frc != HB_OK) { hb_lut_free(out); return frc; }
+    frc = build_fsm(tree, nodes, out);
+    if (frc != HB_OK) { hb_lut_free(out); return frc; }
+    return HB_OK;
+}
+
+/* ---- byte-step transducer -----------------------------------------------------
+ * The reference's CPU jump table (framework/jumptableapproach.c:40-99) keys its rows
+ * by the partial-codeword prefix and emits symbols; this one keys them by the
+ * internal tree node, consumes exactly 8 bits per step and only counts the codewords
+ * that end inside them, which is all the sync kernel needs. */
+static int build_fsm(const hb_node *tree, int nodes, hb_lut *out) {
+    out->fsm_states = 0;
+    out->fsm = NULL;
+    out->fsm_bstep = NULL;
+    memset(out->fsm_depth, 0, sizeof(out->fsm_depth));
+    /* number the internal nodes breadth first from the root */
+    int32_t *state_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)nodes);
+    int32_t *node_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)nodes);
+    if (!state_of || !node_of) { free(state_of); free(node_of); return HB_ERR_NOMEM; }
+    for (int i = 0; i < nodes; i++) state_of[i] = -1;
+    uint32_t ns = 0;
+    uint8_t *depth = (uint8_t *)calloc((size_t)nodes, 1);
+    if (!depth) { free(state_of); free(node_of); return HB_ERR_NOMEM; }
+    state_of[0] = 0; node_of[ns++] = 0;
+    for (uint32_t q = 0; q < ns; q++) {
+        const hb_node *nd = &tree[node_of[q]];
+        int32_t ch[2] = { nd->izero, nd->ione };
+        for (int k = 0; k < 2; k++)
+            if (!is_leaf(&tree[ch[k]])) {
+                state_of[ch[k]] = (int32_t)ns;
+                depth[ns] = (uint8_t)(depth[q] + 1);   /* indexed by state */
+                node_of[ns++] = ch[k];
+            }
+    }
+    if (ns > HB_FSM_MAX_STATES) { free(state_of); free(node_of); free(depth); return HB_OK; }
+    out->fsm = (uint16_t *)malloc(sizeof(uint16_t) * 256 * (size_t)ns);
+    out->fsm_bstep = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (size_t)ns);
+    if (!out->fsm || !out->fsm_bstep) { free(state_of); free(node_of); free(depth); return HB_ERR_NOMEM; }
+    for (uint32_t s = 0; s < ns; s++) {
+        out->fsm_depth[s] = depth[s];
+        for (uint32_t bit = 0; bit < 2; bit++) {
+            int32_t c = bit ? tree[node_of[s]].ione : tree[node_of[s]].izero;
+            out->fsm_bstep[2 * s + bit] = is_leaf(&tree[c]) ? (uint16_t)0x100u : (uint16_t)state_of[c];
+        }
+        for (uint32_t b = 0; b < 256; b++) {
+            int32_t node = node_of[s];
+            uint32_t ends = 0;
+            for (int i = 0; i < 8; i++) {
+                node = ((b >> i) & 1u) ? tree[node].ione : tree[node].izero;
+                if (is_leaf(&tree[node])) { ends++; node = 0; }
+            }
+            out->fsm[s * 256 + b] = (uint16_t)(((uint32_t)state_of[node] << 8) | ends);
+        }
+    }
+    out->fsm_states = ns;
+    free(state_of); free(node_of); free(depth);
     return HB_OK;
 }
 
@@ -240,6 +297,10 @@ void hb_lut_free(hb_lut *lut) {
     free(lut->entries);
     free(lut->stab);
     free(lut->etab);
+    free(lut->fsm);
+    free(lut->fsm_bstep);
+    lut->fsm = lut->fsm_bstep = NULL;
+    lut->fsm_states = 0;
     lut->entries = NULL;
     lut->stab = lut->etab = NULL;
     lut->n_entries = 0;

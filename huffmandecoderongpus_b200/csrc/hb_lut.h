@@ -31,6 +31,12 @@ typedef struct hb_lut {
      * bundled encoder: code bits LSB-first in stream order */
     uint32_t  code[256];
     uint8_t   codelen[256];
+    /* byte-step transducer (hb_format.h); fsm_states == 0 when the tree has more
+     * than HB_FSM_MAX_STATES internal nodes (the probe-based sync path is used) */
+    uint32_t  fsm_states;
+    uint16_t *fsm;         /* fsm_states * 256 entries */
+    uint16_t *fsm_bstep;   /* fsm_states * 2 entries */
+    uint8_t   fsm_depth[256];
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the

@@ -79,6 +79,14 @@ const char *hb_last_error(const hb_ctx *ctx);
 /* words_per_thread: 4, 8 or 16 32-bit words per subsequence (0 = default);
  * ctas_per_sm: persistent CTAs per SM (0 = occupancy-derived). */
 int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
+/* Which sync kernel resolves the chains of full tiles: HB_SYNC_AUTO picks the
+ * byte-step transducer kernel whenever the code table has one (every tree with at
+ * most 256 internal nodes that is not a fixed-length code), HB_SYNC_PROBE forces the
+ * multi-symbol probe kernel (the only path for other trees and for partial tiles).
+ * Both produce identical records; the knob exists for A/B measurement and tests. */
+#define HB_SYNC_AUTO  0
+#define HB_SYNC_PROBE 1
+int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 int  hb_ctx_sync(hb_ctx *ctx);
 /* hb_decode_host cuts streams of at least two chunks into chunks of this many
  * compressed bytes (rounded to whole tiles) and overlaps upload, decode and

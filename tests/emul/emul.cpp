@@ -44,6 +44,8 @@ struct Emul {
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
     hb_tables tbS, tbE; uint32_t maxlen, minlen;
+    hb_fsm fsm; bool have_fsm = false; int sync_mode = 0;   /* 0 probe, 1 transducer on full tiles, 2 both + compare */
+    uint64_t fsm_tiles = 0, fsm_mismatch = 0;
     std::vector<uint16_t> subs;
     std::vector<uint32_t> tmaps;
     std::vector<uint64_t> wmaps, cmaps, cprefix;
@@ -154,6 +156,85 @@ struct Emul {
                 if ((m & 31u) != X0) st.hyp_unmerged++;
             }
             tmaps[(uint64_t)tile * 32 + t] = m;
+        }
+    }
+
+    /* mirrors hb_fsm_sync_kernel, one FULL tile (one group of T threads) */
+    void sync_tile_fsm(uint32_t tile) {
+        std::vector<uint16_t> s_rec(WPT * T, 0);
+        std::vector<uint32_t> s_cs(T, 0), s_exit(T, 0), st_in(T, 0);
+        std::vector<std::array<uint32_t, WPT + 1>> W(T);
+        std::vector<std::array<uint32_t, WPT>> R(T);
+        const uint64_t tbase = (uint64_t)tile * (T * WPT);
+        for (int t = 0; t < T; t++) {
+            uint32_t w[WPT + 1], rec[WPT];
+            load(tbase + (uint64_t)t * WPT, w);
+            for (int j = 0; j <= WPT; j++) W[t][j] = w[j];
+            hb_fsm_walk<WPT>(fsm, w, 0u, rec);
+            for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
+            s_exit[t] = hb_frec_state(rec[WPT - 1]);
+        }
+        uint64_t rounds = 0;
+        for (;;) {
+            bool any = false;
+            std::vector<uint32_t> new_exit(s_exit);
+            for (int t = 1; t < T; t++) {
+                const uint32_t sn = s_exit[t - 1];
+                if (sn != st_in[t]) {
+                    st_in[t] = sn;
+                    uint32_t w[WPT + 1], rec[WPT];
+                    for (int j = 0; j <= WPT; j++) w[j] = W[t][j];
+                    for (int j = 0; j < WPT; j++) rec[j] = R[t][j];
+                    if (hb_fsm_rewalk<WPT>(fsm, w, sn, rec)) any = true;
+                    for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
+                    new_exit[t] = hb_frec_state(rec[WPT - 1]);
+                }
+            }
+            rounds++;
+            if (!any) break;
+            s_exit = new_exit;
+        }
+        st.rounds_total += rounds;
+        st.rounds_max = std::max<uint64_t>(st.rounds_max, rounds);
+        uint32_t E0 = 0, X0 = 0, d0 = 0;
+        for (int t = 0; t < T; t++) {
+            uint32_t ends = 0;
+            for (int j = 0; j < WPT; j++) { ends += hb_frec_ends(R[t][j]); s_rec[j * T + t] = (uint16_t)R[t][j]; }
+            const uint32_t d_in = fsm.depth[st_in[t]], d_out = fsm.depth[hb_frec_state(R[t][WPT - 1])];
+            uint32_t e = 0;
+            if (d_in) e = hb_fsm_fwd(tbS.slow, words[tbase + (uint64_t)t * WPT - 1], W[t][0], d_in);
+            subs[(uint64_t)tile * T + t] = hb_sub_pack(e, ends - (d_in ? 1u : 0u) + (d_out ? 1u : 0u));
+            if (t == T - 1) { X0 = hb_fsm_fwd(tbS.slow, W[t][WPT - 1], W[t][WPT], d_out); d0 = d_out; }
+            s_cs[t] = E0;
+            E0 += ends;
+        }
+        auto word = [&](uint32_t i) -> uint32_t { return tbase + i < nwords ? words[tbase + i] : 0u; };
+        for (uint32_t t = 0; t < 32; t++) {
+            uint32_t m = hb_map_pack32(X0, E0 + (d0 ? 1u : 0u));
+            if (t > 0 && t < maxlen) {
+                m = hb_fsm_hyp_walk<WPT, T>(fsm, tbS.slow, word, s_rec.data(), s_cs.data(), E0, X0, d0, t);
+                if ((m & 31u) != X0) st.hyp_unmerged++;
+            }
+            tmaps[(uint64_t)tile * 32 + t] = m;
+        }
+        fsm_tiles++;
+    }
+
+    /* dispatch of launch_map in hb_api.cu */
+    void sync_all() {
+        const bool use_fsm = sync_mode != 0 && have_fsm && minlen != maxlen;
+        const uint32_t n_full = use_fsm ? (uint32_t)(bits_own / TS) : 0u;
+        for (uint32_t tile = 0; tile < ntiles; tile++) {
+            if (tile < n_full) {
+                sync_tile_fsm(tile);
+                if (sync_mode == 2) {   /* the probe kernel must produce the very same records */
+                    std::vector<uint16_t> a(subs.begin() + (size_t)tile * T, subs.begin() + (size_t)(tile + 1) * T);
+                    std::vector<uint32_t> b(tmaps.begin() + (size_t)tile * 32, tmaps.begin() + (size_t)(tile + 1) * 32);
+                    sync_tile(tile);
+                    if (!std::equal(a.begin(), a.end(), subs.begin() + (size_t)tile * T)) fsm_mismatch++;
+                    if (!std::equal(b.begin(), b.end(), tmaps.begin() + (size_t)tile * 32)) fsm_mismatch++;
+                }
+            } else sync_tile(tile);
         }
     }
 
@@ -312,8 +393,13 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                const uint32_t *stab, const uint32_t *etab, uint32_t wf,
                const uint32_t *words, uint64_t nwords, uint64_t bits_own, uint64_t bits_avail,
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
-               uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win) {
+               uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
+               int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
+               const uint16_t *fsm_bstep) {
     Emul<WPT, T> E;
+    E.sync_mode = sync_mode;
+    E.have_fsm = fsm_states != 0;
+    E.fsm = hb_fsm{fsm_tab, 0u, fsm_depth, fsm_bstep};
     memset(&E.st, 0, sizeof(E.st));
     E.words = words; E.nwords = nwords; E.bits_own = bits_own; E.bits_avail = bits_avail;
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
@@ -325,7 +411,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.subs.assign((size_t)E.ntiles * T, 0);
     E.tmaps.assign((size_t)E.ntiles * 32, 0);
     E.st.tiles = E.ntiles;
-    for (uint32_t tile = 0; tile < E.ntiles; tile++) E.sync_tile(tile);
+    E.sync_all();
     E.scan_up();
     if (E.ntiles == 0) for (int e = 0; e < 32; e++) E.shard_map[e] = (uint64_t)e;
     if (shard_map) memcpy(shard_map, E.shard_map, sizeof(E.shard_map));
@@ -344,6 +430,8 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
         if (result) memcpy(result, res, sizeof(res));
     }
     if (E.st.long_probes >> 63) rc = -100;   /* fast and slow word walks disagreed */
+    if (E.fsm_mismatch) rc = -101;           /* transducer and probe sync kernels disagreed */
+    if (sync_mode && E.have_fsm && minlen != maxlen && E.fsm_tiles != bits_own / E.TS) rc = -102;
     if (stats) *stats = E.st;
     return rc;
 }
@@ -353,12 +441,15 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         const uint32_t *words, uint64_t nwords, uint64_t bits_own,
                         uint64_t bits_avail, int wpt, int T, int have_entry, uint32_t entry,
                         uint64_t base, uint8_t *out, uint64_t out_capacity, uint64_t *shard_map,
-                        uint64_t *result, emul_stats *stats, uint32_t emit_win) {
+                        uint64_t *result, emul_stats *stats, uint32_t emit_win,
+                        int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
+                        const uint8_t *fsm_depth, const uint16_t *fsm_bstep) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
-                          shard_map, result, stats, emit_win)
+                          shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
+                          fsm_depth, fsm_bstep)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

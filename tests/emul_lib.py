@@ -41,7 +41,8 @@ def lib():
                                C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
-                               C.c_void_p, C.POINTER(Stats), C.c_uint32]
+                               C.c_void_p, C.POINTER(Stats), C.c_uint32,
+                               C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -55,8 +56,10 @@ def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
 
 
 def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=True,
-        out_capacity=None, out_offset=0, emit_win=0):
-    """Returns (out bytes, shard_map[32], result[4], stats dict, rc)."""
+        out_capacity=None, out_offset=0, emit_win=0, sync_mode=2):
+    """Returns (out bytes, shard_map[32], result[4], stats dict, rc).
+    sync_mode: 0 = probe sync kernel only, 1 = transducer kernel on full tiles (the
+    product's default dispatch), 2 = both, failing (rc -101) unless they agree."""
     cap = int(out_capacity if out_capacity is not None else bits_own + 64)
     raw = np.zeros(cap + 64 + out_offset, dtype=np.uint8)
     out = raw[out_offset:]
@@ -67,10 +70,15 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
     words = np.ascontiguousarray(words, dtype=np.uint32)
     stab = np.ascontiguousarray(lut["stab"], dtype=np.uint32)
     etab = np.ascontiguousarray(lut["etab"], dtype=np.uint32)
+    fsm = np.ascontiguousarray(lut["fsm"], dtype=np.uint16)
+    fdepth = np.ascontiguousarray(lut["fsm_depth"], dtype=np.uint8)
+    fbstep = np.ascontiguousarray(lut["fsm_bstep"], dtype=np.uint16)
     rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"],
                         stab.ctypes.data, etab.ctypes.data, lut["wf"], words.ctypes.data,
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
-                        out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win)
+                        out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win,
+                        sync_mode, lut["fsm_states"], fsm.ctypes.data, fdepth.ctypes.data,
+                        fbstep.ctypes.data)
     return out, smap, res, st.as_dict(), rc
 
 

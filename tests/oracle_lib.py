@@ -265,3 +265,47 @@ def ref_decode(st: Stream, approach: str = "simpleDecode", param: int | None = N
         p = C.c_int(param)
         getattr(lib, approach)(C.byref(cd), C.byref(ucd), C.byref(p))
     return out[:usize]
+
+
+# ---- hand-made codes for tests and probes (not reference code) ----------------
+def tree_from_lengths(lengths):
+    """canonical-ish complete prefix tree for the given code lengths (Kraft sum 1)"""
+    syms = sorted(range(len(lengths)), key=lambda s: (lengths[s], s))
+    nodes = [[0, -1, -1]]
+    codes = {}
+    code, prev = 0, 0
+    for s in syms:
+        code <<= (lengths[s] - prev)
+        prev = lengths[s]
+        v = 0
+        for i in range(lengths[s] - 1, -1, -1):
+            b = (code >> i) & 1
+            nxt = nodes[v][1 + b]
+            if nxt == -1:
+                nodes.append([0, -1, -1])
+                nxt = len(nodes) - 1
+                nodes[v][1 + b] = nxt
+            v = nxt
+        nodes[v][0] = s
+        codes[s] = [(code >> i) & 1 for i in range(lengths[s] - 1, -1, -1)]
+        code += 1
+    t = np.zeros(len(nodes), dtype=NODE_DTYPE)
+    for i, (sym, a, b) in enumerate(nodes):
+        t[i] = (sym, a, b)
+    return t, codes
+
+
+def encode_with_codes(codes, syms):
+    lens = np.array([len(codes[s]) for s in range(len(codes))])
+    total = int(lens[syms].sum())
+    bits = np.zeros(total + 64, dtype=np.uint8)
+    pos = np.concatenate([[0], np.cumsum(lens[syms])[:-1]])
+    maxl = int(lens.max())
+    table = np.zeros((len(codes), maxl), dtype=np.uint8)
+    for s, c in codes.items():
+        table[s, : len(c)] = c
+    for k in range(maxl):
+        m = lens[syms] > k
+        bits[pos[m] + k] = table[syms[m], k]
+    data = np.packbits(bits, bitorder="little")
+    return np.concatenate([data, np.zeros(32, np.uint8)]), total

@@ -182,3 +182,85 @@ def test_emit_in_several_windows(shape, win):
             assert rc == 0 and int(res[0]) == st.usize
             assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
             assert not out[st.usize:].any()
+
+
+def _bit_walk(tree, node, bits):
+    """reference semantics (framework/mainrun.c:38-55) from an arbitrary node: returns
+    (node after the bits, symbols completed)"""
+    ends = 0
+    for b in bits:
+        node = int(tree[node]["ione"] if b else tree[node]["izero"])
+        if tree[node]["izero"] == -1:
+            ends += 1
+            node = 0
+    return node, ends
+
+
+@pytest.mark.parametrize("name", ["hello", "paper1", "world192", "ecoli", "fib"])
+def test_transducer_table(name):
+    """hb_lut.c build_fsm against a bit-serial walk of the node array: states are the
+    internal nodes (root = 0), an entry is (state after 8 bits, codewords ended)."""
+    tree = hb.Model(hb.MODEL_FIBONACCI).huff_file_cpu(seed=1, n=10)[0].tree if name == "fib" else _stream(name).tree
+    lut = hb.build_lut(tree)
+    ns = lut["fsm_states"]
+    internal = [i for i in range(tree.shape[0]) if tree[i]["izero"] != -1]
+    assert ns == len(internal) <= 256
+    # recover the node of every state by walking the 1-bit table from the root
+    node_of = {0: 0}
+    todo = [0]
+    while todo:
+        s = todo.pop()
+        for bit in (0, 1):
+            r = int(lut["fsm_bstep"][2 * s + bit])
+            child = int(tree[node_of[s]]["ione"] if bit else tree[node_of[s]]["izero"])
+            leaf = tree[child]["izero"] == -1
+            assert bool(r >> 8) == bool(leaf)
+            if not leaf and (r & 0xFF) not in node_of:
+                node_of[r & 0xFF] = child
+                todo.append(r & 0xFF)
+    assert len(node_of) == ns
+    state_of = {v: k for k, v in node_of.items()}
+    rng = np.random.default_rng(7)
+    for s in range(ns):
+        d = 0
+        v = node_of[s]
+        # depth = distance from the root
+        depth = {0: 0}
+        stack = [0]
+        while stack and v not in depth:
+            u = stack.pop()
+            for c in (int(tree[u]["izero"]), int(tree[u]["ione"])):
+                if c != -1 and c not in depth:
+                    depth[c] = depth[u] + 1
+                    stack.append(c)
+        assert lut["fsm_depth"][s] == depth[v]
+        for b in (rng.integers(0, 256, 24).tolist() + [0, 255]):
+            node, ends = _bit_walk(tree, v, [(b >> i) & 1 for i in range(8)])
+            ent = int(lut["fsm"][s * 256 + b])
+            assert ent >> 8 == state_of[node] and (ent & 0xFF) == ends, (s, b)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(8, 256), (2, 8)])
+def test_sync_paths(mode, shape):
+    """probe kernel only / transducer kernel on full tiles (product dispatch) / both
+    with their records compared tile by tile"""
+    st = _stream("news")
+    got, stats, rc = E.decode(st, *shape, sync_mode=mode)
+    assert rc == 0 and O.sha256(got) == O.CORPORA["news"][2]
+
+
+@pytest.mark.parametrize("lengths", [[2, 2, 2, 4, 4, 4, 4], [7] * 64 + [8] * 128, [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12],
+                                     [3, 3, 3, 3, 3, 3, 3, 3]])
+@pytest.mark.parametrize("shape", [(4, 256), (1, 4)])
+def test_badly_synchronising_codes(lengths, shape):
+    """codes whose chains merge late or never (all-even lengths, nearly fixed length,
+    minimum length 1, exactly fixed length): many stitch rounds, unmerged hypotheses"""
+    tree, codes = O.tree_from_lengths(lengths)
+    rng = np.random.default_rng(len(lengths))
+    syms = rng.integers(0, len(lengths), 40000 if shape[1] == 256 else 3000).astype(np.uint8)
+    data, bits = O.encode_with_codes(codes, syms)
+    st = O.Stream(tree, data, bits, syms.size)
+    assert np.array_equal(O.simple_decode(st), syms)
+    got, stats, rc = E.decode(st, *shape)
+    assert rc == 0 and np.array_equal(got, syms)

@@ -270,3 +270,45 @@ def test_full_size_round_trip(dev, kind, log2n, wpt):
     c.close()
     del comp, out
     torch.cuda.empty_cache()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wpt", [4, 8, 16])
+@pytest.mark.parametrize("name", ["paper1", "world192", "kjv", "bible"])
+def test_sync_paths_agree(dev, name, wpt):
+    """The transducer sync kernel (default on full tiles) and the probe sync kernel
+    must give the same bytes, symbol count and shard map."""
+    f = _stream(name)
+    outs = []
+    for path in ("auto", "probe"):
+        c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
+        c.set_sync_path(path)
+        cb = hb.Codebook(c, f.tree)
+        got, res, _ = _decode_dev(c, cb, f, dev)
+        comp = _to_dev(f.data, f.nbytes, dev)
+        d_map = torch.zeros(32, dtype=torch.int64, device=dev)
+        hb.shard_map(c, cb, comp.data_ptr(), comp.numel(), f.bits, f.bits, d_map.data_ptr())
+        c.sync()
+        outs.append((got, res["n_symbols"], res["launches"], d_map.cpu().numpy().copy()))
+        cb.close()
+        c.close()
+    assert O.sha256(outs[0][0]) == O.CORPORA[name][2]
+    assert outs[0][1] == outs[1][1] == f.usize
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][3], outs[1][3])
+    assert outs[0][2] >= outs[1][2]   # the transducer path adds a launch when a partial tile remains
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lengths", [[2, 2, 2, 4, 4, 4, 4], [7] * 64 + [8] * 128,
+                                     [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12], [3] * 8])
+def test_badly_synchronising_codes(ctx, dev, lengths):
+    tree, codes = O.tree_from_lengths(lengths)
+    rng = np.random.default_rng(len(lengths))
+    syms = rng.integers(0, len(lengths), 1 << 20).astype(np.uint8)
+    data, bits = O.encode_with_codes(codes, syms)
+    f = hb.HuffFile(tree, data, bits, syms.size)
+    cb = hb.Codebook(ctx, tree)
+    got, res, _ = _decode_dev(ctx, cb, f, dev)
+    assert res["n_symbols"] == syms.size and np.array_equal(got, syms)
+    cb.close()
