@@ -64,7 +64,8 @@ class LutC(C.Structure):
                 ("stab", C.POINTER(C.c_uint32)), ("etab", C.POINTER(C.c_uint32)),
                 ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256),
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
-                ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256)]
+                ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
+                ("fsm_pstep", C.c_uint16 * 256)]
 
 
 class RefCompressedData(C.Structure):
@@ -206,6 +207,7 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "fsm_bstep": (np.ctypeslib.as_array(lut.fsm_bstep, shape=(ns * 2,)).copy() if ns
                           else np.zeros(2, np.uint16)),
             "fsm_depth": np.array(lut.fsm_depth, dtype=np.uint8),
+            "fsm_pstep": np.array(lut.fsm_pstep, dtype=np.uint16),
             "entries": np.ctypeslib.as_array(lut.entries, shape=(lut.n_entries,)).copy(),
             "w1": lut.w1, "maxlen": lut.maxlen, "minlen": lut.minlen, "n_leaves": lut.n_leaves,
             "wf": lut.wf,

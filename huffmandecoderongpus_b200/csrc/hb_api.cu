@@ -18,7 +18,7 @@ struct hb_codebook {
     hb_ctx *ctx;
     hb_lut lut;        /* host copy (entries kept for the encoder / tests) */
     uint32_t *d_lut;
-    uint8_t *d_fsm;    /* [fsm u16 x states*256][depth u8 x 256][bstep u16 x states*2], or NULL */
+    uint8_t *d_fsm;    /* [fsm u16 x states*256][depth u8 x 256][pstep u16 x 256], or NULL */
     double implied_avg_len;   /* sum over leaves of 2^-len * len */
 };
 
@@ -250,13 +250,13 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         e = cudaMemcpyAsync(cb->d_lut + n1 + nf, cb->lut.etab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && cb->lut.fsm_states) {
         const size_t ns = cb->lut.fsm_states;
-        e = cudaMalloc((void **)&cb->d_fsm, ns * 512 + 256 + ns * 4);
+        e = cudaMalloc((void **)&cb->d_fsm, ns * 512 + 256 + 512);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(cb->d_fsm, cb->lut.fsm, ns * 512, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(cb->d_fsm + ns * 512, cb->lut.fsm_depth, 256, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(cb->d_fsm + ns * 512 + 256, cb->lut.fsm_bstep, ns * 4, cudaMemcpyHostToDevice, ctx->stream);
+            e = cudaMemcpyAsync(cb->d_fsm + ns * 512 + 256, cb->lut.fsm_pstep, 512, cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -395,9 +395,9 @@ static int launch_fsm_sync(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_a
     hb_fsm_args fa;
     fa.tab = (const uint16_t *)cb->d_fsm;
     fa.depth = cb->d_fsm + ns * 512;
-    fa.bstep = (const uint16_t *)(cb->d_fsm + ns * 512 + 256);
+    fa.pstep = (const uint16_t *)(cb->d_fsm + ns * 512 + 256);
     fa.nstates = (uint32_t)ns;
-    const size_t table_bytes = ns * 512 + 256;
+    const size_t table_bytes = ns * 512 + 256 + 512;
     int occ[3] = {0, 0, 0}, rc;
     size_t smem[3] = {0, 0, 0};
     if ((rc = try_fsm_geometry<WPT, 1>(ctx, table_bytes, &occ[0], &smem[0]))) return rc;

@@ -432,7 +432,7 @@ struct hb_fsm {
     const uint16_t *tab;     /* fsm[state * 256 + byte] (host emulation) */
     uint32_t tab_saddr;      /* its shared-state-space address (device) */
     const uint8_t *depth;    /* fsm_depth[state] */
-    const uint16_t *bstep;   /* fsm_bstep[2 * state + bit] */
+    const uint16_t *pstep;   /* fsm_pstep[(1 << r) + bits]: root entry for a step of r < 8 bits */
 };
 
 /* entry for (state in bits 15:8 of ent, byte i of w) */
@@ -499,7 +499,7 @@ HB_HD uint32_t hb_fsm_fwd(const hb_lutref &slow, uint32_t prev, uint32_t next, u
 }
 
 /* Chain of a non-zero tile entry offset e through a FULL tile (T * WPT words):
- * bit steps to the next byte boundary, byte steps to the next word boundary, then
+ * one partial step to the next byte boundary, byte steps to the next word boundary, then
  * word by word until its state equals the hypothesis-0 chain's recorded state (exit
  * and remaining count are then those of hypothesis 0) or the tile ends.
  * recs[j * T + t]: converged records of hypothesis 0; cs[t]: exclusive prefix over
@@ -509,15 +509,14 @@ template <int WPT, int T, class WordFn>
 HB_HD uint32_t hb_fsm_hyp_walk(const hb_fsm &f, const hb_lutref &slow, const WordFn &word,
                                const uint16_t *recs, const uint32_t *cs, uint32_t E0, uint32_t X0,
                                uint32_t d0, uint32_t e) {
-    uint32_t pos = e, n = 0, st = 0;
+    uint32_t pos = e, n = 0, ent = 0;
     const uint32_t w0 = word(0);
-    while (pos & 7u) {
-        const uint32_t r = f.bstep[2u * st + ((w0 >> pos) & 1u)];
-        n += r >> 8;
-        st = r & 0xffu;
-        pos++;
+    if (pos & 7u) {
+        const uint32_t r = 8u - (pos & 7u);
+        ent = f.pstep[(1u << r) + ((w0 >> pos) & ((1u << r) - 1u))];
+        n = ent & 0xffu;
+        pos += r;
     }
-    uint32_t ent = st << 8;
     while (pos & 31u) {
 #ifdef __CUDA_ARCH__
         uint16_t v;

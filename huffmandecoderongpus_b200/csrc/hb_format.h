@@ -28,6 +28,8 @@
  *   fsm[s * 256 + b] (u16), b = the next 8 stream bits, bit 0 first:
  *       [15:8] state after the 8 bits, [3:0] number of codewords that END inside them
  *   fsm_depth[s]  = bits of the unfinished codeword already consumed in state s
- *   fsm_bstep[2 * s + bit] (u16): [7:0] next state, bit 8 = this bit ended a codeword */
+ *   fsm_bstep[2 * s + bit] (u16): [7:0] next state, bit 8 = this bit ended a codeword
+ *   fsm_pstep[(1 << r) + x] (u16), r = 1..7: the root's entry for a step of only r
+ *       bits x (same packing) -- aligns a chain that starts inside a byte          */
 #define HB_FSM_MAX_STATES 256
 #endif

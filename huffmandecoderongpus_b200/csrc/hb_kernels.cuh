@@ -218,7 +218,7 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
  * HB_T threads, each working on its own tile behind its own named barrier. */
 struct hb_fsm_args {
     const uint16_t *tab;     /* nstates * 256 */
-    const uint16_t *bstep;   /* nstates * 2 */
+    const uint16_t *pstep;   /* 256 */
     const uint8_t *depth;    /* 256 */
     uint32_t nstates;
 };
@@ -281,12 +281,12 @@ __global__ void __launch_bounds__(G * HB_T, (G == 1 ? 6 : (G == 2 ? 3 : 1)))
 hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
                    uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
     constexpr int T = HB_T;
-    constexpr uint32_t S = 32u * WPT;
     extern __shared__ __align__(16) uint32_t smem[];
     uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem);                  /* nstates * 256 */
     uint8_t *s_depth = reinterpret_cast<uint8_t *>(smem + fa.nstates * 128u);   /* 256 */
+    uint16_t *s_pstep = reinterpret_cast<uint16_t *>(smem + fa.nstates * 128u + 64u);   /* 256 */
     const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
-    uint32_t *s_grp = smem + fa.nstates * 128u + 64u + g * hb_fsm_group_words<WPT>();
+    uint32_t *s_grp = smem + fa.nstates * 128u + 192u + g * hb_fsm_group_words<WPT>();
     uint16_t *s_rec = reinterpret_cast<uint16_t *>(s_grp);                 /* WPT * T records */
     uint32_t *s_cs = s_grp + WPT * T / 2;                                  /* T: prefix of END counts */
     uint32_t *s_exit = s_cs + T;                                           /* T: state behind each subsequence */
@@ -296,20 +296,24 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
         const uint4 *src = reinterpret_cast<const uint4 *>(fa.tab);
         uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
         for (uint32_t i = threadIdx.x; i < fa.nstates * 32u; i += G * T) dst[i] = __ldg(src + i);
-        for (uint32_t i = threadIdx.x; i < 256u; i += G * T) s_depth[i] = __ldg(fa.depth + i);
+        for (uint32_t i = threadIdx.x; i < 256u; i += G * T) {
+            s_depth[i] = __ldg(fa.depth + i);
+            s_pstep[i] = __ldg(fa.pstep + i);
+        }
     }
     __syncthreads();
     hb_fsm f;
     f.tab = s_tab;
     f.tab_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_tab));
     f.depth = s_depth;
-    f.bstep = fa.bstep;
+    f.pstep = s_pstep;
     const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
 
-    for (uint32_t tile = blockIdx.x * G + g; tile < ntiles_full; tile += gridDim.x * G) {
+    uint32_t tile = blockIdx.x * G + g;
+    uint32_t w[WPT + 1];
+    if (tile < ntiles_full) hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+    while (tile < ntiles_full) {
         const uint64_t wbase = (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT;
-        uint32_t w[WPT + 1];
-        hb_load_words<WPT>(a, wbase, w);
 
         /* chain of the guess "a codeword starts at bit 0 of my subsequence" */
         uint32_t rec[WPT];
@@ -349,6 +353,10 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
             s_warp[12] = hb_fsm_fwd(slow, w[WPT - 1], w[WPT], d_out);
             s_warp[13] = d_out;
         }
+        /* the words are dead from here on: fetch the next tile's now, so that the loads
+         * fly during the scan, the hypothesis walks and the barriers */
+        const uint32_t next = tile + gridDim.x * G;
+        if (next < ntiles_full) hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
         uint32_t E0;
         s_cs[t] = hb_group_exscan(ends, s_warp, bar, t, &E0);
         hb_group_sync(bar);
@@ -365,6 +373,7 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
         hb_group_sync(bar);
+        tile = next;
     }
 }
 

@@ -240,6 +240,17 @@ static int build_fsm(const hb_node *tree, int nodes, hb_lut *out) {
             out->fsm[s * 256 + b] = (uint16_t)(((uint32_t)state_of[node] << 8) | ends);
         }
     }
+    memset(out->fsm_pstep, 0, sizeof(out->fsm_pstep));
+    for (uint32_t r = 1; r < 8; r++)
+        for (uint32_t x = 0; x < (1u << r); x++) {
+            int32_t node = 0;
+            uint32_t ends = 0;
+            for (uint32_t i = 0; i < r; i++) {
+                node = ((x >> i) & 1u) ? tree[node].ione : tree[node].izero;
+                if (is_leaf(&tree[node])) { ends++; node = 0; }
+            }
+            out->fsm_pstep[(1u << r) + x] = (uint16_t)(((uint32_t)state_of[node] << 8) | ends);
+        }
     out->fsm_states = ns;
     free(state_of); free(node_of); free(depth);
     return HB_OK;

@@ -37,6 +37,7 @@ typedef struct hb_lut {
     uint16_t *fsm;         /* fsm_states * 256 entries */
     uint16_t *fsm_bstep;   /* fsm_states * 2 entries */
     uint8_t   fsm_depth[256];
+    uint16_t  fsm_pstep[256];
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the

@@ -395,11 +395,11 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_bstep) {
+               const uint16_t *fsm_pstep) {
     Emul<WPT, T> E;
     E.sync_mode = sync_mode;
     E.have_fsm = fsm_states != 0;
-    E.fsm = hb_fsm{fsm_tab, 0u, fsm_depth, fsm_bstep};
+    E.fsm = hb_fsm{fsm_tab, 0u, fsm_depth, fsm_pstep};
     memset(&E.st, 0, sizeof(E.st));
     E.words = words; E.nwords = nwords; E.bits_own = bits_own; E.bits_avail = bits_avail;
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
@@ -443,13 +443,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t base, uint8_t *out, uint64_t out_capacity, uint64_t *shard_map,
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
-                        const uint8_t *fsm_depth, const uint16_t *fsm_bstep) {
+                        const uint8_t *fsm_depth, const uint16_t *fsm_pstep) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_bstep)
+                          fsm_depth, fsm_pstep)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

@@ -72,13 +72,13 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
     etab = np.ascontiguousarray(lut["etab"], dtype=np.uint32)
     fsm = np.ascontiguousarray(lut["fsm"], dtype=np.uint16)
     fdepth = np.ascontiguousarray(lut["fsm_depth"], dtype=np.uint8)
-    fbstep = np.ascontiguousarray(lut["fsm_bstep"], dtype=np.uint16)
+    fpstep = np.ascontiguousarray(lut["fsm_pstep"], dtype=np.uint16)
     rc = lib().emul_run(ent.ctypes.data, lut["w1"], lut["maxlen"], lut["minlen"],
                         stab.ctypes.data, etab.ctypes.data, lut["wf"], words.ctypes.data,
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
                         out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win,
                         sync_mode, lut["fsm_states"], fsm.ctypes.data, fdepth.ctypes.data,
-                        fbstep.ctypes.data)
+                        fpstep.ctypes.data)
     return out, smap, res, st.as_dict(), rc
 
 

@@ -238,6 +238,11 @@ def test_transducer_table(name):
             node, ends = _bit_walk(tree, v, [(b >> i) & 1 for i in range(8)])
             ent = int(lut["fsm"][s * 256 + b])
             assert ent >> 8 == state_of[node] and (ent & 0xFF) == ends, (s, b)
+    for r in range(1, 8):   # partial steps from the root
+        for x in range(1 << r):
+            node, ends = _bit_walk(tree, 0, [(x >> i) & 1 for i in range(r)])
+            ent = int(lut["fsm_pstep"][(1 << r) + x])
+            assert ent >> 8 == state_of[node] and (ent & 0xFF) == ends, (r, x)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
