@@ -621,13 +621,23 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
 
-    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    /* software pipeline: the next tile's words, record and output base are fetched as
+     * soon as this tile's words are dead (after its last decode window), so that the
+     * loads fly during the copy-out, the barriers and the next scan */
+    uint32_t tile = blockIdx.x, nwin = 0;
+    uint32_t w[WPT + 1];
+    uint16_t sub = 0;
+    uint64_t B = 0;
+    if (tile < a.ntiles) {
+        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+        sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
+        B = tile_base[tile];
+    }
+    while (tile < a.ntiles) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
-        const uint64_t B = tile_base[tile];
-        uint32_t w[WPT + 1];
-        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-        const uint16_t sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
+        const uint32_t next = tile + gridDim.x;
+        const uint64_t Bt = B;
 
         const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
         uint32_t nk;
@@ -636,13 +646,10 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
         /* symbols past the shard's valid total (a cut-off last codeword) are not written */
         uint32_t nvalid = nk;
-        if (B >= total_valid) nvalid = 0;
-        else if (B + nk > total_valid) nvalid = (uint32_t)(total_valid - B);
-        if (B + nvalid > out_capacity) {
-            if (t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
-            __syncthreads();
-            continue;
-        }
+        if (Bt >= total_valid) nvalid = 0;
+        else if (Bt + nk > total_valid) nvalid = (uint32_t)(total_valid - Bt);
+        const bool full_out = Bt + nvalid > out_capacity;
+        if (full_out && t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
 
         /* The staging buffer holds `win` bytes of tile output plus one thread's
          * worth of overhang; a tile whose output is larger (data far more
@@ -651,26 +658,37 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
          * [p*win, (p+1)*win); their slices are contiguous, so it copies out
          * [end of window p-1's threads, end of its own threads). */
         uint32_t lo_b = 0;
-        for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+        for (uint32_t wb = 0; !full_out && (wb == 0 || wb < nk); wb += win, nwin++) {
             const bool mine = c && o >= wb && o - wb < win;
-            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
-            if (t == 0) s_warp[15] = nk;                     /* default: last window */
+            const bool last_win = wb + win >= nk;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + Bt + wb) & 15u);
+            uint32_t *s_hi = s_warp + 14 + (nwin & 1u);     /* alternating slot: no barrier after the copy-out */
+            if (t == 0) {
+                /* the previous window's bulk store must have read the staging buffer */
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                *s_hi = nk;                                  /* default: last window */
+            }
             __syncthreads();
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
                 if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, dst);
                 else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
-                if (o + c - wb >= win && o + c < nk) s_warp[15] = o + c;   /* I am the window's last thread */
+                if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
+            }
+            if (last_win && next < a.ntiles) {
+                hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
+                sub = subs[(uint64_t)next * T + t];
+                B = tile_base[next];
             }
             __syncthreads();
-            uint32_t hi_b = s_warp[15];
+            uint32_t hi_b = *s_hi;
             if (hi_b > nvalid) hi_b = nvalid;
             if (lo_b < hi_b) {
                 /* staging -> global: s_out[al + (b - wb)] -> out[B + b].  The staging index
                  * is congruent to the global address mod 16, so the 16-byte-aligned middle
                  * goes out as ONE bulk asynchronous copy (TMA, cp.async.bulk) issued by a
                  * single thread; the partial first / last vectors are stored byte-wise. */
-                uint8_t *gbase = out + B + wb - al;          /* 16-byte aligned */
+                uint8_t *gbase = out + Bt + wb - al;          /* 16-byte aligned */
                 const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
                 const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
                 if (a0 < a1) {
@@ -685,15 +703,21 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                         if (begb + i < a0) gbase[begb + i] = s_out[begb + i];
                         if (a1 + i < endb) gbase[a1 + i] = s_out[a1 + i];
                     }
-                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 } else {
                     for (uint32_t i = begb + t; i < endb; i += T) gbase[i] = s_out[i];   /* < 32 bytes */
                 }
             }
             lo_b = hi_b > lo_b ? hi_b : lo_b;
-            __syncthreads();
         }
+        if (full_out && next < a.ntiles) {
+            hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
+            sub = subs[(uint64_t)next * T + t];
+            B = tile_base[next];
+        }
+        tile = next;
     }
+    /* the staging buffer must outlive the last bulk store's reads */
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 #endif /* HB_KERNELS_CUH_ */
