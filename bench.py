@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--workload", default="english1g", choices=list(WORKLOADS))
     ap.add_argument("--wpt", type=int, default=0, help="words per thread (0 = library default)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words"],
+                    help="staging stores: bytes (E-table), words (E64-table), auto (by mean codeword length)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe"],
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
@@ -236,6 +238,7 @@ def main():
     ctx = hb.Context(local, stream=torch.cuda.current_stream().cuda_stream,
                      words_per_thread=args.wpt, ctas_per_sm=args.ctas_per_sm)
     ctx.set_sync_path(args.sync_path)
+    ctx.set_emit_path(args.emit_path)
     model = hb.Model(kind)
     cb = hb.Codebook(ctx, model.tree)
 
@@ -405,7 +408,7 @@ def main():
             "config": {"workload": args.workload, "description": desc, "seed": SEED,
                        "symbols_total": n_total, "compressed_bytes_total": int(nbytes_total),
                        "bits_total": int(bits_total), "max_code_length": model.maxlen,
-                       "words_per_thread": args.wpt or 8, "sync_path": args.sync_path,
+                       "words_per_thread": args.wpt or 8, "sync_path": args.sync_path, "emit_path": args.emit_path,
                        "parallelism": f"byte-range shards x{world}, 1 NCCL all-gather of 32-entry maps" if world > 1 else "single GPU",
                        "l2": "inputs and outputs larger than L2 (no flush needed)",
                        "compressed_input_GB_per_s": in_gbs},

@@ -65,7 +65,7 @@ class LutC(C.Structure):
                 ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256),
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
-                ("fsm_pstep", C.c_uint16 * 256)]
+                ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32))]
 
 
 class RefCompressedData(C.Structure):
@@ -104,6 +104,7 @@ def lib():
     L.hb_ctx_destroy.restype = None
     L.hb_ctx_configure.argtypes = [vp, i32, i32]
     L.hb_ctx_set_sync_path.argtypes = [vp, i32]
+    L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_sync.argtypes = [vp]
     L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
     L.hb_ctx_timing_begin.argtypes = [vp, i32]
@@ -213,6 +214,7 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "wf": lut.wf,
             "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
             "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
+            "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
     finally:
@@ -266,6 +268,10 @@ class Context:
 
     def configure(self, words_per_thread=0, ctas_per_sm=0):
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
+
+    def set_emit_path(self, path):
+        """"auto" (by the code's mean codeword length), "bytes" or "words" (staging stores)."""
+        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2}[path]), "hb_ctx_set_emit_path")
 
     def set_sync_path(self, path):
         """"auto" (transducer sync kernel on full tiles when the code has one) or "probe"."""

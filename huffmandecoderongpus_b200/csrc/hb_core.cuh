@@ -350,6 +350,161 @@ HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], 
     return n < c ? n : c;
 }
 
+/* ==== emit walk with word-granular stores (E64-table) =========================
+ * Byte stores into the staging buffer cost ~2.2 shared-memory wavefronts each and
+ * the emit kernel is bound by exactly those.  Here the symbols of a probe (up to
+ * three) are shifted into a 4-byte register window `pend` (newest symbol in the top
+ * byte) and a whole 32-bit staging word is stored whenever the symbol count passes
+ * a multiple of four -- counted from the thread's first 4-byte-aligned staging
+ * address, so every stored word lies entirely inside the thread's own slice.
+ *   negk  = -8 * (symbols past that aligned address): its low 5 bits are the funnel
+ *           shift that extracts the completed word from (new symbols : pend), and
+ *           bit 5 flips exactly when a word boundary is passed
+ *   head  : the first h = (-address) & 3 symbols, plus at least one more, go out as
+ *           bytes (at most 3 probes); tail: the 1..4 symbols left in `pend` after word
+ *           WPT-2 and everything decoded in the last word go out as bytes, the latter
+ *           clipped to the chain's symbol count c (a probe there may run into the
+ *           next subsequence).  Probes in words 0..WPT-2 cannot: they end at most 43
+ *           bits into their word.
+ * Requires 4 * maxlen - 1 < 32 * min(4, WPT - 1) so that the head ends in time
+ * (always true for WPT >= 8; WPT = 4 needs maxlen <= 24).                          */
+struct hb_tables64 {
+    const uint32_t *fast;  /* E64-table (host emulation) */
+    uint32_t fast_saddr;   /* its shared-state-space address (device) */
+    uint32_t fmask8;       /* ((1 << wf) - 1) << 3: byte-offset mask */
+    hb_lutref slow;
+};
+
+struct hb_e64 { uint32_t syms, meta; };
+
+HB_HD hb_e64 hb_fast_load64(const hb_tables64 &tb, uint32_t lo3, uint32_t hi3, uint32_t acc) {
+    const uint32_t x = hb_funnel_r(lo3, hi3, acc) & tb.fmask8;
+    hb_e64 en;
+#ifdef __CUDA_ARCH__
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(en.syms), "=r"(en.meta) : "r"(x + tb.fast_saddr));
+#else
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+    en.syms = p[0];
+    en.meta = p[1];
+#endif
+    return en;
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void hb_st32(hb_out_t base, uint32_t idx, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + idx), "r"(v));
+}
+#else
+static inline void hb_st32(hb_out_t base, uint32_t idx, uint32_t v) {
+    for (int i = 0; i < 4; i++) base[idx + i] = (uint8_t)(v >> (8 * i));
+}
+#endif
+
+/* entry standing for one codeword decoded by the single-symbol table */
+HB_HD hb_e64 hb_e64_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, uint32_t pos) {
+    uint32_t sym;
+    const uint32_t len = hb_probe(slow, lo, hi, pos, &sym);
+    hb_e64 en;
+    en.syms = sym;
+    en.meta = 8u | (len << 16) | (1u << 24);
+    return en;
+}
+
+/* keep a loop-invariant value in its register (the compiler otherwise recomputes the
+ * pre-scaled window inside the probe loop to save one) */
+HB_HD uint32_t hb_keep(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+r"(v));
+#endif
+    return v;
+}
+
+/* shift a probe's symbols into the window; store the staging word they complete */
+HB_HD uint32_t hb_e64_push(const hb_e64 &en, uint32_t &pend, uint32_t negk, hb_out_t &wpp) {
+    const uint32_t word = hb_funnel_r(pend, en.syms, negk);
+    const uint32_t negk_n = negk - en.meta;
+    pend = hb_funnel_r(pend, en.syms, en.meta);
+    if ((negk ^ negk_n) & 0x20u) { hb_st32(wpp, 0u, word); wpp += 4; }
+    return negk_n;
+}
+
+/* mis: (staging address of out) & 3.  Returns the number of symbols stored. */
+template <int WPT>
+HB_HD uint32_t hb_emit_fast2(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
+                             uint32_t c, hb_out_t out, uint32_t mis) {
+    const uint32_t h = (0u - mis) & 3u;
+    uint32_t acc = e, pend = 0u, negk = 8u * h;
+    hb_out_t wpp = out + h;                           /* next staging word to store */
+    constexpr int JH = (WPT - 1 < 4) ? WPT - 1 : 4;   /* words in which the head can end */
+#pragma unroll
+    for (int j = 0; j < WPT - 1; j++) {
+        const uint32_t lo = w[j], hi = w[j + 1];
+        const uint32_t lo3 = hb_keep(lo << 3), hi3 = hb_funnel_l(lo, hi, 3);
+        if (j < JH) {
+            while ((acc >> 8) <= h && !(acc & 0xE0u)) {
+                hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
+                if (!(en.meta >> 24)) en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
+                const uint32_t n = acc >> 8, ns = en.meta >> 24;
+                hb_st8(out, n, en.syms);
+                if (ns >= 2u) hb_st8(out, n + 1u, en.syms >> 8);
+                if (ns >= 3u) hb_st8(out, n + 2u, en.syms >> 16);
+                pend = hb_funnel_r(pend, en.syms, en.meta);
+                negk -= en.meta;
+                acc += en.meta >> 16;
+            }
+        }
+        while (!(acc & 0xE0u)) {
+            /* two probes per trip, so that the window state alternates between two
+             * registers instead of being copied every probe */
+            for (;;) {
+                hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
+                const uint32_t nk2 = hb_e64_push(en, pend, negk, wpp);
+                acc = hb_acc_add(acc, en.meta);
+                if (acc & 0xE0u) { negk = nk2; break; }
+                en = hb_fast_load64(tb, lo3, hi3, acc);
+                negk = hb_e64_push(en, pend, nk2, wpp);
+                acc = hb_acc_add(acc, en.meta);
+                if (acc & 0xE0u) break;
+            }
+            if ((acc & 0xffu) < HB_FAST_MARK) break;
+            /* the last entry was the marker: a codeword longer than the table index */
+            acc -= HB_FAST_MARK;
+            const hb_e64 en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
+            negk = hb_e64_push(en, pend, negk, wpp);
+            acc += en.meta >> 16;
+        }
+        acc -= 32u;
+    }
+    {   /* 1..4 symbols still in the window */
+        const uint32_t k = (uint32_t)((out + (acc >> 8)) - wpp);
+        const uint32_t rest = k ? pend >> ((32u - 8u * k) & 31u) : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; i++)
+            if (i < k) hb_st8(wpp, i, rest >> (8u * i));
+    }
+    {   /* last word: byte stores, clipped to c */
+        const uint32_t lo = w[WPT - 1], hi = w[WPT];
+        const uint32_t lo3 = lo << 3, hi3 = hb_funnel_l(lo, hi, 3);
+        for (;;) {
+            while (!(acc & 0xE0u)) {
+                const hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
+                const uint32_t n = acc >> 8, ns = en.meta >> 24;
+                if (ns >= 1u && n < c) hb_st8(out, n, en.syms);
+                if (ns >= 2u && n + 1u < c) hb_st8(out, n + 1u, en.syms >> 8);
+                if (ns >= 3u && n + 2u < c) hb_st8(out, n + 2u, en.syms >> 16);
+                acc = hb_acc_add(acc, en.meta);
+            }
+            if ((acc & 0xffu) < HB_FAST_MARK) break;
+            acc -= HB_FAST_MARK;
+            const hb_e64 en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
+            if ((acc >> 8) < c) hb_st8(out, acc >> 8, en.syms);
+            acc += en.meta >> 16;
+        }
+        acc -= 32u;
+    }
+    return acc >> 8 < c ? acc >> 8 : c;
+}
+
 /* ==== tile-level walks over shared-memory copies ===========================
  * comp: the tile's T*WPT words followed by the first word of the next tile.
  * recs: converged records of the "tile entry offset 0" chain, recs[j*T + t].

@@ -16,9 +16,14 @@
  *                          HB_E_MAXSYM symbols per entry)
  * When not even the first codeword fits (code longer than wf bits) the entry is
  * the marker: nsym = 0, B = HB_FAST_MARK, low half 0; adding it pushes the
- * position byte past any legal value, which ends the probe loop. */
+ * position byte past any legal value, which ends the probe loop.
+ *   E64-table (emit kernel, word-granular stores): two u32 per index,
+ *       lo: [7:0] [15:8] [23:16] first .. third symbol (at most HB_E64_MAXSYM)
+ *       hi: [4:0] = 8 * nsym (a ready-made funnel-shift amount), [23:16] B, [31:24] nsym
+ *                   marker: nsym = 0, B = HB_FAST_MARK, lo = 0 */
 #define HB_FAST_MARK 0xE0u
 #define HB_E_MAXSYM 2
+#define HB_E64_MAXSYM 3
 #define HB_WF_MAX 12               /* widest fast-table index (16 KB per table) */
 
 /* Byte-step transducer of the sync kernel's fast path (the GPU counterpart of the

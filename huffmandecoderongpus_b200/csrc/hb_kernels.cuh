@@ -597,27 +597,38 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 }
 
 /* ------------------------------------------------------------------------- */
+/* Emit kernel, word-granular variant: staging stores of whole 32-bit words through the
+ * E64-table (hb_emit_fast2, three symbols per probe), software-pipelined tile loads,
+ * bulk-store wait deferred to the next window.  Pays off for codes with short codewords
+ * (many symbols per probe); hb_emit_kernel is the general variant. */
 template <int WPT>
-__global__ void __launch_bounds__(HB_T)
-hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
+__global__ void __launch_bounds__(HB_T, 4)
+hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
                uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
-    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* E-table (static: constant address) */
+    constexpr uint32_t EW = 2u;                                  /* words per table entry */
+    constexpr bool E64 = true;
+    __shared__ __align__(16) uint32_t s_fast[EW << HB_WF_MAX];   /* E- or E64-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_warp = smem;                               /* 16 */
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
     const int t = threadIdx.x;
 
-    for (uint32_t i = t; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
+    for (uint32_t i = t; i < (EW << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
     __syncthreads();
     hb_tables tb;
     tb.fast = s_fast;
     tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    hb_tables64 tb64;
+    tb64.fast = s_fast;
+    tb64.fast_saddr = tb.fast_saddr;
+    tb64.fmask8 = ((1u << a.wf) - 1u) << 3;
+    tb64.slow = tb.slow;
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
 
@@ -628,12 +639,17 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     uint32_t w[WPT + 1];
     uint16_t sub = 0;
     uint64_t B = 0;
-    if (tile < a.ntiles) {
+    if (E64 && tile < a.ntiles) {
         hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
         sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
         B = tile_base[tile];
     }
     while (tile < a.ntiles) {
+        if (!E64) {   /* the 6-CTA byte-store variant has no registers to carry them */
+            hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+            sub = subs[(uint64_t)tile * T + t];
+            B = tile_base[tile];
+        }
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
         const uint32_t next = tile + gridDim.x;
@@ -671,11 +687,12 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             __syncthreads();
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, dst);
-                else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
+                if (lim != S) hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
+                else if (E64) hb_emit_fast2<WPT>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                else hb_emit_fast<WPT>(tb, w, e, c, dst);
                 if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
             }
-            if (last_win && next < a.ntiles) {
+            if (E64 && last_win && next < a.ntiles) {
                 hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
                 sub = subs[(uint64_t)next * T + t];
                 B = tile_base[next];
@@ -709,7 +726,7 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             }
             lo_b = hi_b > lo_b ? hi_b : lo_b;
         }
-        if (full_out && next < a.ntiles) {
+        if (E64 && full_out && next < a.ntiles) {
             hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
             sub = subs[(uint64_t)next * T + t];
             B = tile_base[next];
@@ -718,6 +735,106 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     }
     /* the staging buffer must outlive the last bulk store's reads */
     if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------------- */
+template <int WPT>
+__global__ void __launch_bounds__(HB_T)
+hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
+               const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
+               uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t TS = T * S;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* E-table (static: constant address) */
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *s_warp = smem;                               /* 16 */
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
+    const int t = threadIdx.x;
+
+    for (uint32_t i = t; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
+    __syncthreads();
+    hb_tables tb;
+    tb.fast = s_fast;
+    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
+    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    const uint64_t total_valid = result[0];
+    const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
+
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t tile_bit0 = (uint64_t)tile * TS;
+        const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+        const uint64_t B = tile_base[tile];
+        uint32_t w[WPT + 1];
+        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+        const uint16_t sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
+
+        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        uint32_t nk;
+        const uint32_t o = hb_block_exscan(c, s_warp, &nk);
+        const uint32_t lim = sub0 >= a.bits_own ? 0u
+                           : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+        /* symbols past the shard's valid total (a cut-off last codeword) are not written */
+        uint32_t nvalid = nk;
+        if (B >= total_valid) nvalid = 0;
+        else if (B + nk > total_valid) nvalid = (uint32_t)(total_valid - B);
+        if (B + nvalid > out_capacity) {
+            if (t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
+            __syncthreads();
+            continue;
+        }
+
+        /* The staging buffer holds `win` bytes of tile output plus one thread's
+         * worth of overhang; a tile whose output is larger (data far more
+         * compressible than the code table suggests) is emitted in several
+         * windows.  Window p takes the threads whose first byte lies in
+         * [p*win, (p+1)*win); their slices are contiguous, so it copies out
+         * [end of window p-1's threads, end of its own threads). */
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+            const bool mine = c && o >= wb && o - wb < win;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
+            if (t == 0) s_warp[15] = nk;                     /* default: last window */
+            __syncthreads();
+            if (mine) {
+                const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
+                if (lim == S) hb_emit_fast<WPT>(tb, w, e, c, dst);
+                else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
+                if (o + c - wb >= win && o + c < nk) s_warp[15] = o + c;   /* I am the window's last thread */
+            }
+            __syncthreads();
+            uint32_t hi_b = s_warp[15];
+            if (hi_b > nvalid) hi_b = nvalid;
+            if (lo_b < hi_b) {
+                /* staging -> global: s_out[al + (b - wb)] -> out[B + b].  The staging index
+                 * is congruent to the global address mod 16, so the 16-byte-aligned middle
+                 * goes out as ONE bulk asynchronous copy (TMA, cp.async.bulk) issued by a
+                 * single thread; the partial first / last vectors are stored byte-wise. */
+                uint8_t *gbase = out + B + wb - al;          /* 16-byte aligned */
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
+                if (a0 < a1) {
+                    if (t == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(gbase + a0), "r"(s_out_saddr + a0), "r"(a1 - a0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (t >= 32 && t < 64) {                 /* head and tail bytes, one warp */
+                        const uint32_t i = t - 32;
+                        if (begb + i < a0) gbase[begb + i] = s_out[begb + i];
+                        if (a1 + i < endb) gbase[a1 + i] = s_out[a1 + i];
+                    }
+                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                } else {
+                    for (uint32_t i = begb + t; i < endb; i += T) gbase[i] = s_out[i];   /* < 32 bytes */
+                }
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+            __syncthreads();
+        }
+    }
 }
 
 #endif /* HB_KERNELS_CUH_ */

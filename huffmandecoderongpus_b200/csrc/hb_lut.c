@@ -268,10 +268,12 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
     out->wf = wf;
     out->stab = (uint32_t *)malloc(sizeof(uint32_t) * n);
     out->etab = (uint32_t *)malloc(sizeof(uint32_t) * n);
-    if (!out->stab || !out->etab) return HB_ERR_NOMEM;
+    out->e64 = (uint32_t *)malloc(sizeof(uint32_t) * 2 * n);
+    if (!out->stab || !out->etab || !out->e64) return HB_ERR_NOMEM;
     for (uint32_t x = 0; x < n; x++) {
         uint32_t sm = 0, nsym = 0, used = 0;       /* unlimited symbols (S-table) */
         uint32_t e_syms = 0, e_nsym = 0, e_used = 0; /* at most HB_E_MAXSYM (E-table) */
+        uint32_t x_syms = 0, x_nsym = 0, x_used = 0; /* at most HB_E64_MAXSYM (E64-table) */
         uint32_t pos = 0;
         for (;;) {
             int32_t node = 0;
@@ -289,13 +291,22 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
                 e_nsym++;
                 e_used = p;
             }
+            if (x_nsym < HB_E64_MAXSYM) {
+                x_syms |= (uint32_t)tree[node].sym << (8 * x_nsym);
+                x_nsym++;
+                x_used = p;
+            }
             pos = p;
             if (pos >= wf) break;
         }
         if (nsym == 0) {
             out->stab[x] = HB_FAST_MARK << 16;
             out->etab[x] = HB_FAST_MARK << 16;
+            out->e64[2 * x] = 0;
+            out->e64[2 * x + 1] = HB_FAST_MARK << 16;
         } else {
+            out->e64[2 * x] = x_syms;
+            out->e64[2 * x + 1] = (8u * x_nsym) | (x_used << 16) | (x_nsym << 24);
             out->stab[x] = sm | (used << 16) | (nsym << 24);
             out->etab[x] = e_syms | (e_used << 16) | (e_nsym << 24);
         }
@@ -308,6 +319,8 @@ void hb_lut_free(hb_lut *lut) {
     free(lut->entries);
     free(lut->stab);
     free(lut->etab);
+    free(lut->e64);
+    lut->e64 = NULL;
     free(lut->fsm);
     free(lut->fsm_bstep);
     lut->fsm = lut->fsm_bstep = NULL;

@@ -38,6 +38,7 @@ typedef struct hb_lut {
     uint16_t *fsm_bstep;   /* fsm_states * 2 entries */
     uint8_t   fsm_depth[256];
     uint16_t  fsm_pstep[256];
+    uint32_t *e64;         /* E64-table: 2 << wf words (lo, hi interleaved) */
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the

@@ -44,6 +44,7 @@ struct Emul {
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
     hb_tables tbS, tbE; uint32_t maxlen, minlen;
+    hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) when the code length allows */
     hb_fsm fsm; bool have_fsm = false; int sync_mode = 0;   /* 0 probe, 1 transducer on full tiles, 2 both + compare */
     uint64_t fsm_tiles = 0, fsm_mismatch = 0;
     std::vector<uint16_t> subs;
@@ -328,6 +329,11 @@ struct Emul {
             if (before[t] != subs[(size_t)tile * T + t]) st.probes_fix += hb_sub_count(subs[(size_t)tile * T + t]);
     }
 
+    uint32_t emit2(const uint32_t (&w)[WPT + 1], uint32_t e, uint32_t c, uint8_t *dst, uint32_t mis) {
+        if constexpr (WPT >= 2) return hb_emit_fast2<WPT>(tbE64, w, e, c, dst, mis);
+        else return 0;
+    }
+
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
     bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
                    uint64_t total_valid) {
@@ -358,8 +364,13 @@ struct Emul {
                 load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
                 uint8_t *dst = s_out.data() + al + (o - wb);
                 const uint8_t canary = dst[c];
-                uint32_t n = lim == S ? hb_emit_fast<WPT>(tbE, w, e, c, dst)
-                                      : hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
+                constexpr uint32_t head_words = WPT - 1 < 4 ? WPT - 1 : 4;   /* dispatch of launch_emit */
+                const bool e64 = emit_mode == 1 && WPT >= 2 && 4u * maxlen - 1u < 32u * head_words;
+                /* the staging buffer is 16-byte aligned on the device: only the index counts */
+                const uint32_t mis = (al + (o - wb)) & 3u;
+                uint32_t n = lim != S ? hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst)
+                           : e64 ? emit2(w, e, c, dst, mis)
+                                 : hb_emit_fast<WPT>(tbE, w, e, c, dst);
                 if (n != c) return false;                                /* record/chain mismatch */
                 if (dst[c] != canary) return false;                      /* wrote past its slice */
                 st.probes_emit += n;
@@ -395,8 +406,9 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64) {
     Emul<WPT, T> E;
+    E.emit_mode = emit_mode;
     E.sync_mode = sync_mode;
     E.have_fsm = fsm_states != 0;
     E.fsm = hb_fsm{fsm_tab, 0u, fsm_depth, fsm_pstep};
@@ -405,6 +417,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
+    E.tbE64 = hb_tables64{e64, 0u, ((1u << wf) - 1u) << 3, slow};
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
@@ -443,13 +456,14 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t base, uint8_t *out, uint64_t out_capacity, uint64_t *shard_map,
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
-                        const uint8_t *fsm_depth, const uint16_t *fsm_pstep) {
+                        const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
+                        const uint32_t *e64) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep)
+                          fsm_depth, fsm_pstep, emit_mode, e64)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

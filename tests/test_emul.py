@@ -269,3 +269,47 @@ def test_badly_synchronising_codes(lengths, shape):
     assert np.array_equal(O.simple_decode(st), syms)
     got, stats, rc = E.decode(st, *shape)
     assert rc == 0 and np.array_equal(got, syms)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(4, 256), (8, 256), (16, 256)])
+@pytest.mark.parametrize("name", ["book2", "world192"])
+def test_emit_paths(name, mode, shape):
+    """byte-store emit walk (E-table) and word-store walk (E64-table) give the same bytes;
+    every output alignment, so that every head length 0..3 occurs at a slice start"""
+    st = _stream(name)
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    for off in (0, 1, 2, 3):
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_mode=mode, out_offset=off)
+        assert rc == 0 and int(res[0]) == st.usize
+        assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
+        assert not out[st.usize:].any()
+
+
+def test_e64_table():
+    """E64 entries against the E-/S-table semantics: up to three symbols, bits consumed,
+    8 * nsym in the low bits, marker where no codeword fits"""
+    st = _stream("world192")   # 20-bit codes: markers exist
+    lut = hb.build_lut(st.tree)
+    e64 = lut["e64"].reshape(-1, 2)
+    stab = lut["stab"]
+    marks = 0
+    for x in range(1 << lut["wf"]):
+        syms, meta = int(e64[x, 0]), int(e64[x, 1])
+        ns, bits = meta >> 24, (meta >> 16) & 0xFF
+        if (int(stab[x]) >> 24) == 0:
+            assert ns == 0 and bits == 0xE0 and syms == 0
+            marks += 1
+            continue
+        assert 1 <= ns <= 3 and (meta & 0xFFFF) == 8 * ns
+        # walk the tree over the index bits
+        node, pos, got = 0, 0, []
+        while len(got) < ns:
+            node = int(st.tree[node]["ione"] if (x >> pos) & 1 else st.tree[node]["izero"])
+            pos += 1
+            if st.tree[node]["izero"] == -1:
+                got.append(int(st.tree[node]["sym"]))
+                node = 0
+        assert pos == bits and got == [(syms >> (8 * i)) & 0xFF for i in range(ns)]
+    assert marks > 0

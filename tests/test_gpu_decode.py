@@ -312,3 +312,22 @@ def test_badly_synchronising_codes(ctx, dev, lengths):
     got, res, _ = _decode_dev(ctx, cb, f, dev)
     assert res["n_symbols"] == syms.size and np.array_equal(got, syms)
     cb.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wpt", [4, 8, 16])
+@pytest.mark.parametrize("name", ["paper1", "world192", "kjv", "ecoli"])
+def test_emit_paths_agree(dev, name, wpt):
+    """word-granular staging stores (E64-table, default where the code length allows) and
+    byte stores (E-table) give the same bytes, at every output alignment"""
+    f = _stream(name)
+    for path in ("words", "bytes", "auto"):
+        c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
+        c.set_emit_path(path)
+        cb = hb.Codebook(c, f.tree)
+        for off in (0, 1, 2, 3, 7):
+            got, res, raw = _decode_dev(c, cb, f, dev, out_offset=off)
+            assert res["n_symbols"] == f.usize and O.sha256(got) == O.CORPORA[name][2], (path, off)
+            assert not raw[off + f.usize:].any() and not raw[:off].any()
+        cb.close()
+        c.close()
