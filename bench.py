@@ -200,8 +200,8 @@ def main():
     ap.add_argument("--workload", default="english1g", choices=list(WORKLOADS))
     ap.add_argument("--wpt", type=int, default=0, help="words per thread (0 = library default)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words"],
-                    help="staging stores: bytes (E-table), words (E64-table), auto (by mean codeword length)")
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words2", "words3"],
+                    help="staging stores: bytes, whole words with two / three symbols per probe, auto")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe"],
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
@@ -327,7 +327,8 @@ def main():
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
     sync_name = "hb_fsm_sync_kernel" if args.sync_path == "auto" else "hb_sync_kernel"
-    dom_name = {"sync": sync_name, "emit": "hb_emit_kernel"}[dom]
+    emit_name = "hb_emit_kernel" if args.emit_path == "bytes" else "hb_emitw_kernel"
+    dom_name = {"sync": sync_name, "emit": emit_name}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this
     # same command (profiles/r01_traffic.json); only quoted for the configuration it was taken on
@@ -342,7 +343,7 @@ def main():
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": b_alg,
-        "kernel_ms": {sync_name: k_ms["sync"], "hb_scan_*+hb_fix": k_ms["scan"], "hb_emit_kernel": k_ms["emit"]},
+        "kernel_ms": {sync_name: k_ms["sync"], "hb_scan_*+hb_fix": k_ms["scan"], emit_name: k_ms["emit"]},
         "decode_achieved": b_alg / (k_ms["total"] * 1e-3) / 1e9,
         "decode_frac": b_alg / (k_ms["total"] * 1e-3) / 1e9 / peak,
         "kernel_share_of_step": k_ms[dom] / k_ms["total"],

@@ -65,7 +65,8 @@ class LutC(C.Structure):
                 ("code", C.c_uint32 * 256), ("codelen", C.c_uint8 * 256),
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
-                ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32))]
+                ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32)),
+                ("ew", C.POINTER(C.c_uint32))]
 
 
 class RefCompressedData(C.Structure):
@@ -215,6 +216,7 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
             "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
             "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf,)).copy(),
+            "ew": np.ctypeslib.as_array(lut.ew, shape=(1 << lut.wf,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
     finally:
@@ -270,8 +272,10 @@ class Context:
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
 
     def set_emit_path(self, path):
-        """"auto" (by the code's mean codeword length), "bytes" or "words" (staging stores)."""
-        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2}[path]), "hb_ctx_set_emit_path")
+        """staging stores: "bytes", "words2" / "words3" (whole words, two / three symbols per
+        probe) or "auto" (= words3)."""
+        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words2": 2, "words3": 3}[path]),
+               "hb_ctx_set_emit_path")
 
     def set_sync_path(self, path):
         """"auto" (transducer sync kernel on full tiles when the code has one) or "probe"."""

@@ -185,7 +185,7 @@ extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
 }
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
-    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS)) return HB_ERR_ARG;
+    if (!ctx || path < HB_EMIT_AUTO || path > HB_EMIT_WORDS3) return HB_ERR_ARG;
     ctx->emit_path = path;
     return HB_OK;
 }
@@ -245,9 +245,9 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         cb->implied_avg_len = acc;
     }
     cudaSetDevice(ctx->device);
-    /* device layout: [single-symbol LUT][S-table][E-table][E64-table] */
+    /* device layout: [single-symbol LUT][S-table][E-table][E64-table][EW-table] */
     const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
-    size_t bytes = sizeof(uint32_t) * (n1 + 4 * nf);
+    size_t bytes = sizeof(uint32_t) * (n1 + 5 * nf);
     cudaError_t e = cudaMalloc((void **)&cb->d_lut, bytes);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(cb->d_lut, cb->lut.entries, sizeof(uint32_t) * n1, cudaMemcpyHostToDevice, ctx->stream);
@@ -257,6 +257,8 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         e = cudaMemcpyAsync(cb->d_lut + n1 + nf, cb->lut.etab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(cb->d_lut + n1 + 2 * nf, cb->lut.e64, sizeof(uint32_t) * 2 * nf, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cb->d_lut + n1 + 4 * nf, cb->lut.ew, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && cb->lut.fsm_states) {
         const size_t ns = cb->lut.fsm_states;
         e = cudaMalloc((void **)&cb->d_fsm, ns * 512 + 256 + 512);
@@ -504,19 +506,26 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     stage_geometry(cb, WPT, &win, &stage);
     size_t smem = emit_smem_bytes(a.wf, stage);
     int grid = 1;
-    /* word-granular stores need the head of every thread's slice to end within the first
-     * min(4, WPT - 1) words (hb_emit_fast2); otherwise, or on request, byte stores */
-    const uint32_t head_words = WPT - 1 < 4 ? WPT - 1 : 4;
-    /* ... and only pay off when a probe usually holds more than two codewords */
-    const bool e64 = ctx->emit_path != HB_EMIT_BYTES && 4u * a.maxlen - 1u < 32u * head_words &&
-                     (ctx->emit_path == HB_EMIT_WORDS || cb->implied_avg_len < 3.5);
-    if (e64) {
-        ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
-        if ((rc = grid_for(ctx, hb_emit64_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
-        hb_emit64_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
-            ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-            (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
-            (uint32_t *)(misc + 36));
+    /* staging stores: whole words, three symbols per probe (measured best on both bench
+     * workloads: english1g 0.775 ms vs 0.98 with two per probe and 0.81 with byte stores);
+     * the other variants on request */
+    if (ctx->emit_path != HB_EMIT_BYTES) {
+        const bool e64 = ctx->emit_path != HB_EMIT_WORDS2;
+        if (e64) {
+            ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
+            if ((rc = grid_for(ctx, hb_emitw_kernel<WPT, true>, smem, a.ntiles, &grid))) return rc;
+            hb_emitw_kernel<WPT, true><<<grid, HB_T, smem, ctx->stream>>>(
+                ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
+                (uint32_t *)(misc + 36));
+        } else {
+            ae.fast = a.fast + ((size_t)4 << a.wf);   /* EW-table */
+            if ((rc = grid_for(ctx, hb_emitw_kernel<WPT, false>, smem, a.ntiles, &grid))) return rc;
+            hb_emitw_kernel<WPT, false><<<grid, HB_T, smem, ctx->stream>>>(
+                ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
+                (uint32_t *)(misc + 36));
+        }
     } else {
         ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
         if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;

@@ -350,44 +350,58 @@ HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], 
     return n < c ? n : c;
 }
 
-/* ==== emit walk with word-granular stores (E64-table) =========================
- * Byte stores into the staging buffer cost ~2.2 shared-memory wavefronts each and
- * the emit kernel is bound by exactly those.  Here the symbols of a probe (up to
- * three) are shifted into a 4-byte register window `pend` (newest symbol in the top
- * byte) and a whole 32-bit staging word is stored whenever the symbol count passes
- * a multiple of four -- counted from the thread's first 4-byte-aligned staging
- * address, so every stored word lies entirely inside the thread's own slice.
- *   negk  = -8 * (symbols past that aligned address): its low 5 bits are the funnel
- *           shift that extracts the completed word from (new symbols : pend), and
- *           bit 5 flips exactly when a word boundary is passed
- *   head  : the first h = (-address) & 3 symbols, plus at least one more, go out as
- *           bytes (at most 3 probes); tail: the 1..4 symbols left in `pend` after word
- *           WPT-2 and everything decoded in the last word go out as bytes, the latter
- *           clipped to the chain's symbol count c (a probe there may run into the
- *           next subsequence).  Probes in words 0..WPT-2 cannot: they end at most 43
- *           bits into their word.
- * Requires 4 * maxlen - 1 < 32 * min(4, WPT - 1) so that the head ends in time
- * (always true for WPT >= 8; WPT = 4 needs maxlen <= 24).                          */
+/* ==== emit walk with word-granular stores ======================================
+ * Byte stores into the staging buffer cost ~2.2 shared-memory wavefronts each, and the
+ * emit kernel is bound by exactly those.  Here the symbols of a probe are shifted into
+ * a 4-byte register window `pend` (newest symbol in the top byte) and a whole 32-bit
+ * staging word is stored whenever the running byte count passes a multiple of four.
+ *   posk : 8 * (bytes since the 4-byte-aligned address at or below the thread's first
+ *          byte) in its low bits.  Bit 5 flips exactly when a staging word completes;
+ *          the low 5 bits are the funnel shift that assembles that word from
+ *          (new symbols : pend).
+ *   The first word a thread stores may start before its slice (lanes below its first
+ *   byte hold zeros): those lanes are the LAST bytes of the left neighbour, which every
+ *   thread therefore keeps in registers and stores byte-wise after a barrier (the
+ *   `tail`).  No other staging byte is written by two threads.
+ *   Only probes in the last word can run into the next subsequence; there the symbols
+ *   pushed are clipped to the chain's count c.
+ * Two table formats (hb_format.h): E64 (LDS.64, three symbols per probe: codes with
+ * short codewords) and EW (LDS.32, two symbols per probe).                           */
 struct hb_tables64 {
-    const uint32_t *fast;  /* E64-table (host emulation) */
+    const uint32_t *fast;  /* E64- or EW-table (host emulation) */
     uint32_t fast_saddr;   /* its shared-state-space address (device) */
-    uint32_t fmask8;       /* ((1 << wf) - 1) << 3: byte-offset mask */
+    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << 3 (E64) or << 2 (EW) */
     hb_lutref slow;
 };
 
-struct hb_e64 { uint32_t syms, meta; };
+/* one probe: symbols (first in the low byte), sh (low 5 bits = 8 * nsym; added to posk
+ * as a whole), adv (low byte = bits consumed or HB_FAST_MARK; E64: bits 8+ = nsym) */
+struct hb_pe { uint32_t syms, sh, adv; };
 
-HB_HD hb_e64 hb_fast_load64(const hb_tables64 &tb, uint32_t lo3, uint32_t hi3, uint32_t acc) {
-    const uint32_t x = hb_funnel_r(lo3, hi3, acc) & tb.fmask8;
-    hb_e64 en;
+template <bool E64>
+HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, uint32_t acc) {
+    const uint32_t x = hb_funnel_r(los, his, acc) & tb.fmask;
+    hb_pe p;
+    if (E64) {
+        uint32_t lo, hi;
 #ifdef __CUDA_ARCH__
-    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(en.syms), "=r"(en.meta) : "r"(x + tb.fast_saddr));
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(x + tb.fast_saddr));
 #else
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
-    en.syms = p[0];
-    en.meta = p[1];
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+        lo = q[0];
+        hi = q[1];
 #endif
-    return en;
+        p.syms = lo; p.sh = hi; p.adv = hi >> 16;
+    } else {
+        uint32_t ent;
+#ifdef __CUDA_ARCH__
+        asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(x + tb.fast_saddr));
+#else
+        ent = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+#endif
+        p.syms = ent >> 16; p.sh = ent; p.adv = ent >> 8;   /* adv bits 8+ are junk: only the position byte is used */
+    }
+    return p;
 }
 
 #ifdef __CUDA_ARCH__
@@ -400,14 +414,13 @@ static inline void hb_st32(hb_out_t base, uint32_t idx, uint32_t v) {
 }
 #endif
 
-/* entry standing for one codeword decoded by the single-symbol table */
-HB_HD hb_e64 hb_e64_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, uint32_t pos) {
+/* probe standing for one codeword decoded by the single-symbol table */
+HB_HD hb_pe hb_pe_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, uint32_t pos) {
     uint32_t sym;
     const uint32_t len = hb_probe(slow, lo, hi, pos, &sym);
-    hb_e64 en;
-    en.syms = sym;
-    en.meta = 8u | (len << 16) | (1u << 24);
-    return en;
+    hb_pe p;
+    p.syms = sym; p.sh = 8u; p.adv = len | 0x100u;
+    return p;
 }
 
 /* keep a loop-invariant value in its register (the compiler otherwise recomputes the
@@ -420,89 +433,84 @@ HB_HD uint32_t hb_keep(uint32_t v) {
 }
 
 /* shift a probe's symbols into the window; store the staging word they complete */
-HB_HD uint32_t hb_e64_push(const hb_e64 &en, uint32_t &pend, uint32_t negk, hb_out_t &wpp) {
-    const uint32_t word = hb_funnel_r(pend, en.syms, negk);
-    const uint32_t negk_n = negk - en.meta;
-    pend = hb_funnel_r(pend, en.syms, en.meta);
-    if ((negk ^ negk_n) & 0x20u) { hb_st32(wpp, 0u, word); wpp += 4; }
-    return negk_n;
+HB_HD uint32_t hb_push(uint32_t syms, uint32_t sh, uint32_t &pend, uint32_t posk, hb_out_t &wpp) {
+    const uint32_t word = hb_funnel_l(pend, syms, posk);
+    const uint32_t posk_n = posk + sh;
+    pend = hb_funnel_r(pend, syms, sh);
+    if ((posk ^ posk_n) & 0x20u) { hb_st32(wpp, 0u, word); wpp += 4; }
+    return posk_n;
 }
 
-/* mis: (staging address of out) & 3.  Returns the number of symbols stored. */
-template <int WPT>
-HB_HD uint32_t hb_emit_fast2(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
-                             uint32_t c, hb_out_t out, uint32_t mis) {
-    const uint32_t h = (0u - mis) & 3u;
-    uint32_t acc = e, pend = 0u, negk = 8u * h;
-    hb_out_t wpp = out + h;                           /* next staging word to store */
-    constexpr int JH = (WPT - 1 < 4) ? WPT - 1 : 4;   /* words in which the head can end */
+struct hb_tail { hb_out_t at; uint32_t k, bytes; };   /* k bytes (low first) to store at `at` after the barrier */
+
+/* mis: (staging address of out) & 3 */
+template <int WPT, bool E64>
+HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
+                            uint32_t c, hb_out_t out, uint32_t mis) {
+    constexpr uint32_t SC = E64 ? 3u : 2u;            /* window pre-scale: log2(bytes per entry) */
+    uint32_t acc = e, pend = 0u, posk = 8u * mis;
+    hb_out_t wpp = out - mis;                         /* next staging word to store */
 #pragma unroll
     for (int j = 0; j < WPT - 1; j++) {
         const uint32_t lo = w[j], hi = w[j + 1];
-        const uint32_t lo3 = hb_keep(lo << 3), hi3 = hb_funnel_l(lo, hi, 3);
-        if (j < JH) {
-            while ((acc >> 8) <= h && !(acc & 0xE0u)) {
-                hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
-                if (!(en.meta >> 24)) en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
-                const uint32_t n = acc >> 8, ns = en.meta >> 24;
-                hb_st8(out, n, en.syms);
-                if (ns >= 2u) hb_st8(out, n + 1u, en.syms >> 8);
-                if (ns >= 3u) hb_st8(out, n + 2u, en.syms >> 16);
-                pend = hb_funnel_r(pend, en.syms, en.meta);
-                negk -= en.meta;
-                acc += en.meta >> 16;
-            }
-        }
-        while (!(acc & 0xE0u)) {
-            /* two probes per trip, so that the window state alternates between two
-             * registers instead of being copied every probe */
+        const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
+        for (;;) {
+            /* two probes per trip: posk alternates between two registers instead of
+             * being copied every probe */
             for (;;) {
-                hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
-                const uint32_t nk2 = hb_e64_push(en, pend, negk, wpp);
-                acc = hb_acc_add(acc, en.meta);
-                if (acc & 0xE0u) { negk = nk2; break; }
-                en = hb_fast_load64(tb, lo3, hi3, acc);
-                negk = hb_e64_push(en, pend, nk2, wpp);
-                acc = hb_acc_add(acc, en.meta);
+                hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                const uint32_t pk2 = hb_push(p.syms, p.sh, pend, posk, wpp);
+                acc += p.adv;
+                if (acc & 0xE0u) { posk = pk2; break; }
+                p = hb_probe_words<E64>(tb, los, his, acc);
+                posk = hb_push(p.syms, p.sh, pend, pk2, wpp);
+                acc += p.adv;
                 if (acc & 0xE0u) break;
             }
             if ((acc & 0xffu) < HB_FAST_MARK) break;
-            /* the last entry was the marker: a codeword longer than the table index */
+            /* the last entry was the marker (no symbols, no count): a codeword longer
+             * than the table index starts at the position before it */
             acc -= HB_FAST_MARK;
-            const hb_e64 en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
-            negk = hb_e64_push(en, pend, negk, wpp);
-            acc += en.meta >> 16;
+            const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc & 0xffu);
+            posk = hb_push(p.syms, p.sh, pend, posk, wpp);
+            acc += p.adv;
+            if (acc & 0xE0u) break;
         }
         acc -= 32u;
     }
-    {   /* 1..4 symbols still in the window */
-        const uint32_t k = (uint32_t)((out + (acc >> 8)) - wpp);
-        const uint32_t rest = k ? pend >> ((32u - 8u * k) & 31u) : 0u;
-#pragma unroll
-        for (uint32_t i = 0; i < 4u; i++)
-            if (i < k) hb_st8(wpp, i, rest >> (8u * i));
-    }
-    {   /* last word: byte stores, clipped to c */
+    {   /* last word: the symbols pushed are clipped to c */
         const uint32_t lo = w[WPT - 1], hi = w[WPT];
-        const uint32_t lo3 = lo << 3, hi3 = hb_funnel_l(lo, hi, 3);
+        const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
+        uint32_t n = (uint32_t)(wpp - out) + ((posk >> 3) & 3u);   /* symbols pushed so far */
         for (;;) {
             while (!(acc & 0xE0u)) {
-                const hb_e64 en = hb_fast_load64(tb, lo3, hi3, acc);
-                const uint32_t n = acc >> 8, ns = en.meta >> 24;
-                if (ns >= 1u && n < c) hb_st8(out, n, en.syms);
-                if (ns >= 2u && n + 1u < c) hb_st8(out, n + 1u, en.syms >> 8);
-                if (ns >= 3u && n + 2u < c) hb_st8(out, n + 2u, en.syms >> 16);
-                acc = hb_acc_add(acc, en.meta);
+                const hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                const uint32_t ns = (p.sh >> 3) & 3u;
+                uint32_t sh = p.sh;
+                if (n + ns > c) sh = 8u * (n < c ? c - n : 0u);
+                posk = hb_push(p.syms, sh, pend, posk, wpp);
+                n += ns;
+                acc += p.adv;
             }
             if ((acc & 0xffu) < HB_FAST_MARK) break;
             acc -= HB_FAST_MARK;
-            const hb_e64 en = hb_e64_single(tb.slow, lo, hi, acc & 0xffu);
-            if ((acc >> 8) < c) hb_st8(out, acc >> 8, en.syms);
-            acc += en.meta >> 16;
+            const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc & 0xffu);
+            posk = hb_push(p.syms, n < c ? 8u : 0u, pend, posk, wpp);
+            n += 1u;
+            acc += p.adv;
         }
-        acc -= 32u;
     }
-    return acc >> 8 < c ? acc >> 8 : c;
+    hb_tail tl;
+    tl.k = (posk >> 3) & 3u;
+    tl.bytes = tl.k ? pend >> ((32u - 8u * tl.k) & 31u) : 0u;
+    tl.at = wpp;
+    return tl;
+}
+
+HB_HD void hb_store_tail(const hb_tail &tl) {
+#pragma unroll
+    for (uint32_t i = 0; i < 3u; i++)
+        if (i < tl.k) hb_st8(tl.at, i, tl.bytes >> (8u * i));
 }
 
 /* ==== tile-level walks over shared-memory copies ===========================

@@ -216,6 +216,12 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
  * stream bits (PRMT, LEA, LDS.U16, IADD), no data-dependent loop, no divergence.
  * A CTA holds ONE copy of the table (up to 128 KB) and G independent groups of
  * HB_T threads, each working on its own tile behind its own named barrier. */
+#ifndef HB_FSM_CTAS1
+#define HB_FSM_CTAS1 6      /* resident CTAs per SM the G = 1 / G = 2 variants are compiled for */
+#endif
+#ifndef HB_FSM_CTAS2
+#define HB_FSM_CTAS2 3
+#endif
 struct hb_fsm_args {
     const uint16_t *tab;     /* nstates * 256 */
     const uint16_t *pstep;   /* 256 */
@@ -277,7 +283,7 @@ __host__ __device__ constexpr uint32_t hb_fsm_group_words() {
 }
 
 template <int WPT, int G>
-__global__ void __launch_bounds__(G * HB_T, (G == 1 ? 6 : (G == 2 ? 3 : 1)))
+__global__ void __launch_bounds__(G * HB_T, (G == 1 ? HB_FSM_CTAS1 : (G == 2 ? HB_FSM_CTAS2 : 1)))
 hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
                    uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
     constexpr int T = HB_T;
@@ -597,20 +603,20 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 }
 
 /* ------------------------------------------------------------------------- */
-/* Emit kernel, word-granular variant: staging stores of whole 32-bit words through the
- * E64-table (hb_emit_fast2, three symbols per probe), software-pipelined tile loads,
- * bulk-store wait deferred to the next window.  Pays off for codes with short codewords
- * (many symbols per probe); hb_emit_kernel is the general variant. */
-template <int WPT>
-__global__ void __launch_bounds__(HB_T, 4)
-hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
+/* Emit kernel, word-granular variant (hb_emit_words): staging stores of whole 32-bit
+ * words assembled in a register window, each thread's last partial word stored
+ * byte-wise after a barrier; software-pipelined tile loads; bulk-store wait deferred to
+ * the next window.  E64 = true: E64-table, three symbols per probe (codes with short
+ * codewords); false: EW-table, two symbols per probe. */
+template <int WPT, bool E64>
+__global__ void __launch_bounds__(HB_T, (E64 ? 4 : 5))
+hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
                uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
-    constexpr uint32_t EW = 2u;                                  /* words per table entry */
-    constexpr bool E64 = true;
+    constexpr uint32_t EW = E64 ? 2u : 1u;                       /* words per table entry */
     __shared__ __align__(16) uint32_t s_fast[EW << HB_WF_MAX];   /* E- or E64-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_warp = smem;                               /* 16 */
@@ -627,7 +633,7 @@ hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     hb_tables64 tb64;
     tb64.fast = s_fast;
     tb64.fast_saddr = tb.fast_saddr;
-    tb64.fmask8 = ((1u << a.wf) - 1u) << 3;
+    tb64.fmask = ((1u << a.wf) - 1u) << (E64 ? 3 : 2);
     tb64.slow = tb.slow;
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
@@ -639,13 +645,13 @@ hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     uint32_t w[WPT + 1];
     uint16_t sub = 0;
     uint64_t B = 0;
-    if (E64 && tile < a.ntiles) {
+    if (tile < a.ntiles) {
         hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
         sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
         B = tile_base[tile];
     }
     while (tile < a.ntiles) {
-        if (!E64) {   /* the 6-CTA byte-store variant has no registers to carry them */
+        if (false) {
             hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
             sub = subs[(uint64_t)tile * T + t];
             B = tile_base[tile];
@@ -685,18 +691,23 @@ hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                 *s_hi = nk;                                  /* default: last window */
             }
             __syncthreads();
+            hb_tail tl;
+            tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
                 if (lim != S) hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
-                else if (E64) hb_emit_fast2<WPT>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
-                else hb_emit_fast<WPT>(tb, w, e, c, dst);
+                else tl = hb_emit_words<WPT, E64>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
                 if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
             }
-            if (E64 && last_win && next < a.ntiles) {
+            if (last_win && next < a.ntiles) {
                 hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
                 sub = subs[(uint64_t)next * T + t];
                 B = tile_base[next];
             }
+            __syncthreads();
+            /* every word store is done: the last, partial word of each slice (its other
+             * lanes belong to the right neighbour, who has just overwritten them) */
+            hb_store_tail(tl);
             __syncthreads();
             uint32_t hi_b = *s_hi;
             if (hi_b > nvalid) hi_b = nvalid;
@@ -726,7 +737,7 @@ hb_emit64_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             }
             lo_b = hi_b > lo_b ? hi_b : lo_b;
         }
-        if (E64 && full_out && next < a.ntiles) {
+        if (full_out && next < a.ntiles) {
             hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
             sub = subs[(uint64_t)next * T + t];
             B = tile_base[next];

@@ -39,6 +39,7 @@ typedef struct hb_lut {
     uint8_t   fsm_depth[256];
     uint16_t  fsm_pstep[256];
     uint32_t *e64;         /* E64-table: 2 << wf words (lo, hi interleaved) */
+    uint32_t *ew;          /* EW-table: 1 << wf words */
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the

@@ -87,15 +87,16 @@ int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
 #define HB_SYNC_AUTO  0
 #define HB_SYNC_PROBE 1
 int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
-/* How the emit kernel fills its staging buffer: HB_EMIT_BYTES = byte stores, two
- * symbols per table probe (every code); HB_EMIT_WORDS = whole 32-bit words, three
- * symbols per probe (needs 4 * maxlen - 1 < 32 * min(4, words_per_thread - 1), else
- * bytes); HB_EMIT_AUTO = words when the code's implied mean codeword length is below
- * 3.5 bits (a probe then usually holds three codewords), bytes otherwise.
+/* How the emit kernel fills its staging buffer:
+ *   HB_EMIT_WORDS2 / HB_EMIT_WORDS3  whole 32-bit words assembled in registers, two /
+ *                   three symbols per table probe (hb_emitw_kernel)
+ *   HB_EMIT_BYTES   byte stores, two symbols per probe (hb_emit_kernel)
+ *   HB_EMIT_AUTO    WORDS3 (the fastest on every workload measured)
  * Identical output; the knob exists for A/B measurement and tests. */
-#define HB_EMIT_AUTO  0
-#define HB_EMIT_BYTES 1
-#define HB_EMIT_WORDS 2
+#define HB_EMIT_AUTO   0
+#define HB_EMIT_BYTES  1
+#define HB_EMIT_WORDS2 2
+#define HB_EMIT_WORDS3 3
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
 int  hb_ctx_sync(hb_ctx *ctx);
 /* hb_decode_host cuts streams of at least two chunks into chunks of this many

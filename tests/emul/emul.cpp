@@ -44,7 +44,7 @@ struct Emul {
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
     hb_tables tbS, tbE; uint32_t maxlen, minlen;
-    hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) when the code length allows */
+    hb_tables64 tbE64, tbEW; int emit_mode = 0;   /* 0 byte stores (E-table), 2 / 3 word stores (EW- / E64-table) */
     hb_fsm fsm; bool have_fsm = false; int sync_mode = 0;   /* 0 probe, 1 transducer on full tiles, 2 both + compare */
     uint64_t fsm_tiles = 0, fsm_mismatch = 0;
     std::vector<uint16_t> subs;
@@ -329,11 +329,6 @@ struct Emul {
             if (before[t] != subs[(size_t)tile * T + t]) st.probes_fix += hb_sub_count(subs[(size_t)tile * T + t]);
     }
 
-    uint32_t emit2(const uint32_t (&w)[WPT + 1], uint32_t e, uint32_t c, uint8_t *dst, uint32_t mis) {
-        if constexpr (WPT >= 2) return hb_emit_fast2<WPT>(tbE64, w, e, c, dst, mis);
-        else return 0;
-    }
-
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
     bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
                    uint64_t total_valid) {
@@ -352,6 +347,7 @@ struct Emul {
             std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
             const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
             uint32_t hi_b = nk;
+            std::vector<hb_tail> tails;   /* hb_emitw_kernel: stored after the barrier that ends the decode */
             for (int t = 0; t < T; t++) {
                 const uint32_t o = off[t], c = cnt[t];
                 const bool mine = c && o >= wb && o - wb < win;
@@ -364,19 +360,24 @@ struct Emul {
                 load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
                 uint8_t *dst = s_out.data() + al + (o - wb);
                 const uint8_t canary = dst[c];
-                constexpr uint32_t head_words = WPT - 1 < 4 ? WPT - 1 : 4;   /* dispatch of launch_emit */
-                const bool e64 = emit_mode == 1 && WPT >= 2 && 4u * maxlen - 1u < 32u * head_words;
                 /* the staging buffer is 16-byte aligned on the device: only the index counts */
                 const uint32_t mis = (al + (o - wb)) & 3u;
-                uint32_t n = lim != S ? hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst)
-                           : e64 ? emit2(w, e, c, dst, mis)
-                                 : hb_emit_fast<WPT>(tbE, w, e, c, dst);
+                uint32_t n = c;
+                if (lim != S) n = hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
+                else if (emit_mode == 0 || WPT < 2) n = hb_emit_fast<WPT>(tbE, w, e, c, dst);
+                else if constexpr (WPT >= 2) {
+                    tails.push_back(emit_mode == 3 ? hb_emit_words<WPT, true>(tbE64, w, e, c, dst, mis)
+                                                   : hb_emit_words<WPT, false>(tbEW, w, e, c, dst, mis));
+                    /* whole words inside the slice plus the tail make exactly c bytes */
+                    if ((uint32_t)((tails.back().at + tails.back().k) - dst) != c) return false;
+                }
                 if (n != c) return false;                                /* record/chain mismatch */
                 if (dst[c] != canary) return false;                      /* wrote past its slice */
                 st.probes_emit += n;
                 trips[t] = n;
                 if (o + c - wb >= win && o + c < nk) hi_b = o + c;
             }
+            for (const hb_tail &tl : tails) hb_store_tail(tl);
             if (hi_b > nvalid) hi_b = nvalid;
             if (lo_b < hi_b) {
                 uint8_t *gbase = out + B + wb - al;
@@ -406,7 +407,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, const uint32_t *ew) {
     Emul<WPT, T> E;
     E.emit_mode = emit_mode;
     E.sync_mode = sync_mode;
@@ -418,6 +419,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE64 = hb_tables64{e64, 0u, ((1u << wf) - 1u) << 3, slow};
+    E.tbEW = hb_tables64{ew, 0u, ((1u << wf) - 1u) << 2, slow};
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
@@ -457,13 +459,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
                         const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
-                        const uint32_t *e64) {
+                        const uint32_t *e64, const uint32_t *ew) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep, emit_mode, e64)
+                          fsm_depth, fsm_pstep, emit_mode, e64, ew)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

@@ -321,7 +321,7 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto"):
+    for path in ("words2", "words3", "bytes", "auto"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         c.set_emit_path(path)
         cb = hb.Codebook(c, f.tree)
