@@ -66,7 +66,8 @@ class LutC(C.Structure):
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
                 ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32)),
-                ("ew", C.POINTER(C.c_uint32))]
+                ("ew", C.POINTER(C.c_uint32)),
+                ("fsm_node", C.c_int32 * 256), ("node_state", C.POINTER(C.c_int32))]
 
 
 class RefCompressedData(C.Structure):
@@ -105,6 +106,7 @@ def lib():
     L.hb_ctx_destroy.restype = None
     L.hb_ctx_configure.argtypes = [vp, i32, i32]
     L.hb_ctx_set_sync_path.argtypes = [vp, i32]
+    L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_sync.argtypes = [vp]
     L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
@@ -324,6 +326,16 @@ class Codebook:
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         lib().hb_codebook_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         self.maxlen, self.minlen, self.w1, self.n_entries = a.value, b.value, c.value, d.value
+
+    def table(self, which):
+        """Device-resident code table copied back to the host: "lut", "stab", "etab", "e64",
+        "ew" (u32 arrays) or "fsm" (u16)."""
+        idx = {"lut": 0, "stab": 1, "etab": 2, "e64": 3, "ew": 4, "fsm": 5}[which]
+        buf = np.zeros(1 << 20, dtype=np.uint8)
+        n = C.c_uint64()
+        _check(lib().hb_codebook_download_table(self.h, idx, buf.ctypes.data, buf.size, C.byref(n)),
+               "hb_codebook_download_table", self.ctx.h)
+        return buf[: n.value].view(np.uint16 if which == "fsm" else np.uint32).copy()
 
     def close(self):
         if self.h:

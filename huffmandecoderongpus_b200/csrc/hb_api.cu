@@ -224,58 +224,81 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
     cb->ctx = ctx;
     cb->d_lut = nullptr;
     cb->d_fsm = nullptr;
-    int rc = hb_lut_build(tree, nodes, 0, 0, &cb->lut);
+    /* host: validation, state numbering, single-symbol table, per-symbol codes; the
+     * multi-symbol tables and the transducer table are built on the device */
+    int rc = hb_lut_build_small(tree, nodes, 0, 0, &cb->lut);
     if (rc != HB_OK) { delete cb; return rc; }
     {   /* expected code length under the code's own implied distribution */
         double acc = 0.0;
-        for (int v = 0, sp = 0; ; ) {
-            /* iterative DFS over the (validated) tree, depth kept alongside */
-            static thread_local int32_t st_node[2 * 64 + 4];
-            static thread_local int st_depth[2 * 64 + 4];
-            st_node[0] = 0; st_depth[0] = 0; sp = 1;
-            while (sp > 0) {
-                v = st_node[--sp];
-                int d = st_depth[sp];
-                if (tree[v].izero == -1) { acc += (double)d / (double)(1ull << d); continue; }
-                st_node[sp] = tree[v].izero; st_depth[sp++] = d + 1;
-                st_node[sp] = tree[v].ione;  st_depth[sp++] = d + 1;
-            }
-            break;
+        for (int i = 0; i < 256; i++) (void)i;
+        /* iterative DFS over the (validated) tree, depth kept alongside */
+        int32_t st_node[2 * 64 + 4];
+        int st_depth[2 * 64 + 4];
+        int sp = 0;
+        st_node[0] = 0; st_depth[0] = 0; sp = 1;
+        while (sp > 0) {
+            const int v = st_node[--sp];
+            const int d = st_depth[sp];
+            if (tree[v].izero == -1) { acc += (double)d / (double)(1ull << d); continue; }
+            st_node[sp] = tree[v].izero; st_depth[sp++] = d + 1;
+            st_node[sp] = tree[v].ione;  st_depth[sp++] = d + 1;
         }
         cb->implied_avg_len = acc;
     }
     cudaSetDevice(ctx->device);
     /* device layout: [single-symbol LUT][S-table][E-table][E64-table][EW-table] */
     const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
-    size_t bytes = sizeof(uint32_t) * (n1 + 5 * nf);
-    cudaError_t e = cudaMalloc((void **)&cb->d_lut, bytes);
+    const size_t ns = cb->lut.fsm_states;
+    /* ONE stream-ordered allocation: [tables][transducer + depth + partial steps][build
+     * inputs: node array, state of every node, node of every state] */
+    const size_t lut_bytes = (sizeof(uint32_t) * (n1 + 5 * nf) + 15) & ~(size_t)15;
+    const size_t fsm_bytes = ns ? ns * 512 + 256 + 512 : 0;
+    const size_t tree_bytes = sizeof(hb_node_abi) * (size_t)nodes;
+    const size_t in_bytes = ((tree_bytes + 15) & ~(size_t)15) + sizeof(int32_t) * ((size_t)nodes + 256);
+    uint8_t *d_all = nullptr, *d_in = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d_all, lut_bytes + fsm_bytes + in_bytes, ctx->stream);
+    if (e == cudaSuccess) {
+        cb->d_lut = (uint32_t *)d_all;
+        cb->d_fsm = ns ? d_all + lut_bytes : nullptr;
+        d_in = d_all + lut_bytes + fsm_bytes;
+    }
+    hb_build_args ba;
+    memset(&ba, 0, sizeof(ba));
+    if (e == cudaSuccess) {
+        ba.tree = (const hb_node_abi *)d_in;
+        int32_t *d_ns = (int32_t *)(d_in + ((tree_bytes + 15) & ~(size_t)15));
+        ba.node_state = d_ns;
+        ba.state_node = d_ns + nodes;
+        ba.nstates = (uint32_t)ns;
+        ba.wf = cb->lut.wf;
+        ba.stab = cb->d_lut + n1;
+        ba.etab = cb->d_lut + n1 + nf;
+        ba.e64 = cb->d_lut + n1 + 2 * nf;
+        ba.ew = cb->d_lut + n1 + 4 * nf;
+        ba.fsm = ns ? (uint16_t *)cb->d_fsm : nullptr;
+        e = cudaMemcpyAsync(d_in, tree, tree_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && ns)
+            e = cudaMemcpyAsync(d_ns, cb->lut.node_state, sizeof(int32_t) * (size_t)nodes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && ns)
+            e = cudaMemcpyAsync(d_ns + nodes, cb->lut.fsm_node, sizeof(int32_t) * 256, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(cb->d_lut, cb->lut.entries, sizeof(uint32_t) * n1, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cb->d_lut + n1, cb->lut.stab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cb->d_lut + n1 + nf, cb->lut.etab, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cb->d_lut + n1 + 2 * nf, cb->lut.e64, sizeof(uint32_t) * 2 * nf, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cb->d_lut + n1 + 4 * nf, cb->lut.ew, sizeof(uint32_t) * nf, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && cb->lut.fsm_states) {
-        const size_t ns = cb->lut.fsm_states;
-        e = cudaMalloc((void **)&cb->d_fsm, ns * 512 + 256 + 512);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(cb->d_fsm, cb->lut.fsm, ns * 512, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(cb->d_fsm + ns * 512, cb->lut.fsm_depth, 256, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(cb->d_fsm + ns * 512 + 256, cb->lut.fsm_pstep, 512, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && ns)
+        e = cudaMemcpyAsync(cb->d_fsm + ns * 512, cb->lut.fsm_depth, 256, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && ns)
+        e = cudaMemcpyAsync(cb->d_fsm + ns * 512 + 256, cb->lut.fsm_pstep, 512, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const size_t entries = nf + ns * 256;
+        hb_build_tables_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, ctx->stream>>>(ba);
+        e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   /* the host arrays are reused */
     if (e != cudaSuccess) {
-        if (cb->d_lut) cudaFree(cb->d_lut);
-        if (cb->d_fsm) cudaFree(cb->d_fsm);
+        if (d_all) cudaFreeAsync(d_all, ctx->stream);
         hb_lut_free(&cb->lut);
         delete cb;
-        return cuda_fail(ctx, e, "codebook upload");
+        return cuda_fail(ctx, e, "codebook build");
     }
     *out = cb;
     return HB_OK;
@@ -284,10 +307,33 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
 extern "C" void hb_codebook_destroy(hb_codebook *cb) {
     if (!cb) return;
     cudaSetDevice(cb->ctx->device);
-    if (cb->d_lut) cudaFree(cb->d_lut);
-    if (cb->d_fsm) cudaFree(cb->d_fsm);
+    if (cb->d_lut) cudaFreeAsync(cb->d_lut, cb->ctx->stream);   /* d_fsm lives in the same allocation */
     hb_lut_free(&cb->lut);
     delete cb;
+}
+
+extern "C" int hb_codebook_download_table(const hb_codebook *cb, int which, void *dst, uint64_t capacity,
+                                          uint64_t *bytes) {
+    if (!cb || !dst || !bytes) return HB_ERR_ARG;
+    hb_ctx *ctx = cb->ctx;
+    const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf, ns = cb->lut.fsm_states;
+    const uint8_t *src = nullptr;
+    size_t n = 0;
+    switch (which) {
+    case HB_TABLE_LUT: src = (const uint8_t *)cb->d_lut; n = 4 * n1; break;
+    case HB_TABLE_S:   src = (const uint8_t *)(cb->d_lut + n1); n = 4 * nf; break;
+    case HB_TABLE_E:   src = (const uint8_t *)(cb->d_lut + n1 + nf); n = 4 * nf; break;
+    case HB_TABLE_E64: src = (const uint8_t *)(cb->d_lut + n1 + 2 * nf); n = 8 * nf; break;
+    case HB_TABLE_EW:  src = (const uint8_t *)(cb->d_lut + n1 + 4 * nf); n = 4 * nf; break;
+    case HB_TABLE_FSM: src = cb->d_fsm; n = ns * 512; break;
+    default: return HB_ERR_ARG;
+    }
+    *bytes = n;
+    if (n > capacity) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HB_OK;
 }
 
 extern "C" int hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,

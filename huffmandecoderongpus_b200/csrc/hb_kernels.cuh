@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "hb_core.cuh"
+#include "huffb200.h"
 
 #define HB_T 256            /* threads per CTA = subsequences per tile */
 #ifndef HB_SYNC_MIN_CTAS
@@ -205,6 +206,79 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
             tmaps[(uint64_t)tile * 32 + t] = m;
         }
         __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Code tables built on the device from the node array (the reference
+ * has a dead precedent in framework/fastgpuOpt1.cu:22-49).  One thread per table entry:
+ * entries [0, 1 << wf) are the four multi-symbol tables (same index, one walk of at most
+ * wf bits), entries after that the transducer table (state, byte).  The host only
+ * validates the tree, numbers the states and builds the small single-symbol table
+ * (hb_lut_build_small); csrc/hb_lut.c keeps the full host construction as the reference
+ * the tests compare this kernel against, entry by entry. */
+struct hb_build_args {
+    const hb_node_abi *tree;      /* reference node array, 12-byte structs */
+    const int32_t *node_state;    /* state of every node, -1 for leaves */
+    const int32_t *state_node;    /* node of every state */
+    uint32_t nstates, wf;
+    uint32_t *stab, *etab, *e64, *ew;
+    uint16_t *fsm;                /* NULL when the tree has no transducer */
+};
+
+__global__ void __launch_bounds__(256)
+hb_build_tables_kernel(hb_build_args b) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t nf = 1u << b.wf;
+    if (i < nf) {
+        const uint32_t x = i;
+        uint32_t sm = 0, nsym = 0, used = 0, syms = 0, pos = 0;
+        uint32_t used2 = 0, used3 = 0;   /* bits used by the first two / three codewords */
+        for (;;) {
+            int32_t node = 0;
+            uint32_t p = pos;
+            while (b.tree[node].izero != -1 && p < b.wf) {
+                node = ((x >> p) & 1u) ? b.tree[node].ione : b.tree[node].izero;
+                p++;
+            }
+            if (b.tree[node].izero != -1) break;      /* next codeword does not fit */
+            sm |= 1u << pos;
+            if (nsym < 3u) syms |= (uint32_t)b.tree[node].sym << (8u * nsym);
+            nsym++;
+            used = p;
+            if (nsym <= 2u) used2 = p;
+            if (nsym <= 3u) used3 = p;
+            pos = p;
+            if (pos >= b.wf) break;
+        }
+        if (nsym == 0) {
+            b.stab[x] = HB_FAST_MARK << 16;
+            b.etab[x] = HB_FAST_MARK << 16;
+            b.e64[2 * x] = 0;
+            b.e64[2 * x + 1] = HB_FAST_MARK << 16;
+            b.ew[x] = HB_FAST_MARK << 8;
+        } else {
+            const uint32_t n2 = nsym < 2u ? nsym : 2u, n3 = nsym < 3u ? nsym : 3u;
+            const uint32_t s2 = syms & (n2 == 2u ? 0xffffu : 0xffu);
+            b.stab[x] = sm | (used << 16) | (nsym << 24);
+            b.etab[x] = s2 | (used2 << 16) | (n2 << 24);
+            b.ew[x] = (8u * n2) | (used2 << 8) | (s2 << 16);
+            b.e64[2 * x] = syms;
+            b.e64[2 * x + 1] = (8u * n3) | (used3 << 16) | (n3 << 24);
+        }
+        return;
+    }
+    const uint32_t k = i - nf;
+    if (b.fsm && k < b.nstates * 256u) {
+        const uint32_t s = k >> 8, byte = k & 255u;
+        int32_t node = b.state_node[s];
+        uint32_t ends = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; bit++) {
+            node = ((byte >> bit) & 1u) ? b.tree[node].ione : b.tree[node].izero;
+            if (b.tree[node].izero == -1) { ends++; node = 0; }
+        }
+        b.fsm[k] = (uint16_t)(((uint32_t)b.node_state[node] << 8) | ends);
     }
 }
 

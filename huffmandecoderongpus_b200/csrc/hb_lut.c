@@ -31,7 +31,7 @@ typedef struct builder {
 
 static int is_leaf(const hb_node *n) { return n->izero == -1 && n->ione == -1; }
 static int build_fast_tables(const hb_node *tree, hb_lut *out);
-static int build_fsm(const hb_node *tree, int nodes, hb_lut *out);
+static int build_fsm(const hb_node *tree, int nodes, hb_lut *out, int with_table);
 
 /* iterative validation: every reachable node is a full internal node or a leaf,
  * indices in range, no node reached twice (=> a tree, no cycles), depth <= 32 */
@@ -154,7 +154,17 @@ static void collect_codes(const hb_node *tree, int32_t node, int depth,
     collect_codes(tree, nd->ione, depth + 1, bits | (depth < 32 ? (1u << depth) : 0u), out, have);
 }
 
+static int lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out, int small);
+
 int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out) {
+    return lut_build(tree, nodes, w1_max, w2_max, out, 0);
+}
+
+int hb_lut_build_small(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out) {
+    return lut_build(tree, nodes, w1_max, w2_max, out, 1);
+}
+
+static int lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out, int small) {
     if (!out) return HB_ERR_ARG;
     memset(out, 0, sizeof(*out));
     if (nodes > (1 << 20)) return HB_ERR_TREE;
@@ -184,9 +194,10 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
     uint8_t have[256];
     memset(have, 0, sizeof(have));
     collect_codes(tree, 0, 0, 0, out, have);
-    int frc = build_fast_tables(tree, out);
+    out->wf = HB_WF_MAX;
+    int frc = small ? HB_OK : build_fast_tables(tree, out);
     if (frc != HB_OK) { hb_lut_free(out); return frc; }
-    frc = build_fsm(tree, nodes, out);
+    frc = build_fsm(tree, nodes, out, !small);
     if (frc != HB_OK) { hb_lut_free(out); return frc; }
     return HB_OK;
 }
@@ -196,8 +207,10 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
  * by the partial-codeword prefix and emits symbols; this one keys them by the
  * internal tree node, consumes exactly 8 bits per step and only counts the codewords
  * that end inside them, which is all the sync kernel needs. */
-static int build_fsm(const hb_node *tree, int nodes, hb_lut *out) {
+static int build_fsm(const hb_node *tree, int nodes, hb_lut *out, int with_table) {
     out->fsm_states = 0;
+    out->node_state = NULL;
+    for (int i = 0; i < 256; i++) out->fsm_node[i] = -1;
     out->fsm = NULL;
     out->fsm_bstep = NULL;
     memset(out->fsm_depth, 0, sizeof(out->fsm_depth));
@@ -221,16 +234,17 @@ static int build_fsm(const hb_node *tree, int nodes, hb_lut *out) {
             }
     }
     if (ns > HB_FSM_MAX_STATES) { free(state_of); free(node_of); free(depth); return HB_OK; }
-    out->fsm = (uint16_t *)malloc(sizeof(uint16_t) * 256 * (size_t)ns);
+    if (with_table) out->fsm = (uint16_t *)malloc(sizeof(uint16_t) * 256 * (size_t)ns);
     out->fsm_bstep = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (size_t)ns);
-    if (!out->fsm || !out->fsm_bstep) { free(state_of); free(node_of); free(depth); return HB_ERR_NOMEM; }
+    if ((with_table && !out->fsm) || !out->fsm_bstep) { free(state_of); free(node_of); free(depth); return HB_ERR_NOMEM; }
     for (uint32_t s = 0; s < ns; s++) {
         out->fsm_depth[s] = depth[s];
+        out->fsm_node[s] = node_of[s];
         for (uint32_t bit = 0; bit < 2; bit++) {
             int32_t c = bit ? tree[node_of[s]].ione : tree[node_of[s]].izero;
             out->fsm_bstep[2 * s + bit] = is_leaf(&tree[c]) ? (uint16_t)0x100u : (uint16_t)state_of[c];
         }
-        for (uint32_t b = 0; b < 256; b++) {
+        for (uint32_t b = 0; with_table && b < 256; b++) {
             int32_t node = node_of[s];
             uint32_t ends = 0;
             for (int i = 0; i < 8; i++) {
@@ -252,7 +266,8 @@ static int build_fsm(const hb_node *tree, int nodes, hb_lut *out) {
             out->fsm_pstep[(1u << r) + x] = (uint16_t)(((uint32_t)state_of[node] << 8) | ends);
         }
     out->fsm_states = ns;
-    free(state_of); free(node_of); free(depth);
+    out->node_state = state_of;
+    free(node_of); free(depth);
     return HB_OK;
 }
 
@@ -327,6 +342,8 @@ void hb_lut_free(hb_lut *lut) {
     lut->e64 = lut->ew = NULL;
     free(lut->fsm);
     free(lut->fsm_bstep);
+    free(lut->node_state);
+    lut->node_state = NULL;
     lut->fsm = lut->fsm_bstep = NULL;
     lut->fsm_states = 0;
     lut->entries = NULL;

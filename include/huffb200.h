@@ -124,6 +124,16 @@ int  hb_dev_download(hb_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes
 int  hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
                         hb_codebook **cb);
 void hb_codebook_destroy(hb_codebook *cb);
+/* Copy one of the device-resident code tables back to the host (tests: the tables are
+ * built by a kernel and compared with csrc/hb_lut.c's host construction). */
+#define HB_TABLE_LUT 0   /* single-symbol multi-level table (built on the host) */
+#define HB_TABLE_S   1
+#define HB_TABLE_E   2
+#define HB_TABLE_E64 3
+#define HB_TABLE_EW  4
+#define HB_TABLE_FSM 5   /* byte-step transducer; 0 bytes when the tree has none */
+int  hb_codebook_download_table(const hb_codebook *cb, int which, void *dst, uint64_t capacity,
+                                uint64_t *bytes);
 int  hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,
                       uint32_t *w1, uint32_t *n_entries);
 

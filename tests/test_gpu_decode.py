@@ -331,3 +331,24 @@ def test_emit_paths_agree(dev, name, wpt):
             assert not raw[off + f.usize:].any() and not raw[:off].any()
         cb.close()
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hello", "paper1", "world192", "ecoli", "fib", "english"])
+def test_device_built_tables_match_host_construction(ctx, name):
+    """hb_build_tables_kernel (one thread per table entry, walking the uploaded node array)
+    against csrc/hb_lut.c's host construction, entry by entry"""
+    if name in ("fib", "english"):
+        tree = hb.Model(hb.MODEL_FIBONACCI if name == "fib" else hb.MODEL_ENGLISH).tree
+    else:
+        tree = _stream(name).tree
+    lut = hb.build_lut(tree)
+    cb = hb.Codebook(ctx, tree)
+    assert np.array_equal(cb.table("lut"), lut["entries"])
+    for key in ("stab", "etab", "e64", "ew"):
+        assert np.array_equal(cb.table(key), lut[key]), key
+    fsm = cb.table("fsm")
+    assert fsm.size == lut["fsm_states"] * 256
+    if fsm.size:
+        assert np.array_equal(fsm, lut["fsm"])
+    cb.close()
