@@ -291,7 +291,7 @@ def tree_from_lengths(lengths):
         code += 1
     t = np.zeros(len(nodes), dtype=NODE_DTYPE)
     for i, (sym, a, b) in enumerate(nodes):
-        t[i] = (sym, a, b)
+        t[i] = (sym & 255, a, b)   # more than 256 leaves: symbols repeat
     return t, codes
 
 

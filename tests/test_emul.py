@@ -313,3 +313,20 @@ def test_e64_table():
                 node = 0
         assert pos == bits and got == [(syms >> (8 * i)) & 0xFF for i in range(ns)]
     assert marks > 0
+
+
+@pytest.mark.parametrize("shape", [(8, 256), (2, 8)])
+def test_tree_with_more_than_256_internal_nodes(shape):
+    """300 leaves (symbols repeat): no transducer table, the probe sync kernel does all tiles"""
+    lengths = [8] * 212 + [9] * 88
+    tree, codes = O.tree_from_lengths(lengths)
+    lut = hb.build_lut(tree)
+    assert lut["fsm_states"] == 0 and tree.shape[0] == 599
+    rng = np.random.default_rng(3)
+    syms = rng.integers(0, 300, 30000)
+    data, bits = O.encode_with_codes(codes, syms)
+    st = O.Stream(tree, data, bits, syms.size)
+    want = (syms & 255).astype(np.uint8)
+    assert np.array_equal(O.simple_decode(st), want)
+    got, stats, rc = E.decode(st, *shape, lut=lut)
+    assert rc == 0 and np.array_equal(got, want)

@@ -352,3 +352,19 @@ def test_device_built_tables_match_host_construction(ctx, name):
     if fsm.size:
         assert np.array_equal(fsm, lut["fsm"])
     cb.close()
+
+
+@pytest.mark.gpu
+def test_tree_with_more_than_256_internal_nodes(ctx, dev):
+    """no transducer table: the probe sync kernel does every tile (dispatch in launch_map)"""
+    lengths = [8] * 212 + [9] * 88
+    tree, codes = O.tree_from_lengths(lengths)
+    rng = np.random.default_rng(3)
+    syms = rng.integers(0, 300, 1 << 20)
+    data, bits = O.encode_with_codes(codes, syms)
+    f = hb.HuffFile(tree, data, bits, syms.size)
+    cb = hb.Codebook(ctx, tree)
+    assert cb.table("fsm").size == 0
+    got, res, _ = _decode_dev(ctx, cb, f, dev)
+    assert res["n_symbols"] == syms.size and np.array_equal(got, (syms & 255).astype(np.uint8))
+    cb.close()
