@@ -220,6 +220,13 @@ HB_HD uint32_t hb_bound(uint32_t lim, uint32_t j) {
     return lim >= 32u * (j + 1u) ? 32u : (lim > 32u * j ? lim - 32u * j : 0u);
 }
 
+/* multi-symbol probes may carry starts into the next word; that is only exact when word
+ * j is fully owned and the next word is fully owned or not owned at all */
+HB_HD bool hb_fast_ok(uint32_t lim, uint32_t j) {
+    const uint32_t left = lim > 32u * j ? lim - 32u * j : 0u;
+    return left >= 64u || left == 32u;
+}
+
 /* Chain of entry offset e through a whole subsequence (WPT words, w[WPT] = first
  * word of the next one): fills rec[j] = (land, cnt) per word. */
 template <int WPT>
@@ -234,10 +241,13 @@ HB_HD void hb_walk(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t l
             rec[j] = hb_rec_pack(land, cnt);
         }
     } else {
+        /* partial subsequence (stream tail): multi-symbol probes wherever they are exact
+         * (hb_fast_ok), one symbol per probe through the global-memory table elsewhere */
 #pragma unroll
         for (int j = 0; j < WPT; j++) {
             uint32_t land, cnt;
-            hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, j), acc, land, cnt);
+            if (hb_fast_ok(lim, j)) hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
+            else hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, j), acc, land, cnt);
             rec[j] = hb_rec_pack(land, cnt);
         }
     }
@@ -257,7 +267,7 @@ HB_HD bool hb_rewalk(const hb_tables &tb, const uint32_t (&w)[WPT + 1], uint32_t
     for (int j = 0; j < WPT; j++) {
         if (!merged) {
             uint32_t land, cnt;
-            if (full) hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
+            if (full || hb_fast_ok(lim, j)) hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
             else hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, j), acc, land, cnt);
             merged = land == hb_rec_land(rec[j]);
             rec[j] = hb_rec_pack(land, cnt);
@@ -505,6 +515,42 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
     tl.bytes = tl.k ? pend >> ((32u - 8u * tl.k) & 31u) : 0u;
     tl.at = wpp;
     return tl;
+}
+
+/* Partial subsequence (stream tail) in the word-store kernel: byte stores, every symbol
+ * clipped to the chain's count c -- which is exactly the number of owned codeword starts,
+ * so probes may run past the owned bits (into the halo or the zero padding) freely. */
+template <int WPT, bool E64>
+HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
+                               uint32_t e, uint32_t c, hb_out_t out) {
+    constexpr uint32_t SC = E64 ? 3u : 2u;
+    uint32_t acc = e & 0xffu, n = 0u;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        if (32u * j < lim) {
+            const uint32_t lo = w[j], hi = w[j + 1];
+            const uint32_t los = lo << SC, his = hb_funnel_l(lo, hi, SC);
+            for (;;) {
+                while (!(acc & 0xE0u)) {
+                    const hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                    const uint32_t ns = (p.sh >> 3) & 3u;
+                    if (ns >= 1u && n < c) hb_st8(out, n, p.syms);
+                    if (ns >= 2u && n + 1u < c) hb_st8(out, n + 1u, p.syms >> 8);
+                    if (ns >= 3u && n + 2u < c) hb_st8(out, n + 2u, p.syms >> 16);
+                    n += ns;
+                    acc = (acc + p.adv) & 0xffu;
+                }
+                if (acc < HB_FAST_MARK) break;
+                acc -= HB_FAST_MARK;
+                const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc);
+                if (n < c) hb_st8(out, n, p.syms);
+                n += 1u;
+                acc = (acc + p.adv) & 0xffu;
+            }
+            acc -= 32u;
+        }
+    }
+    return n < c ? n : c;
 }
 
 HB_HD void hb_store_tail(const hb_tail &tl) {

@@ -769,7 +769,7 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim != S) hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
+                if (lim != S) hb_emit_clipped<WPT, E64>(tb64, w, lim, e, c, dst);
                 else tl = hb_emit_words<WPT, E64>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
                 if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
             }

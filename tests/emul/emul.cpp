@@ -363,7 +363,9 @@ struct Emul {
                 /* the staging buffer is 16-byte aligned on the device: only the index counts */
                 const uint32_t mis = (al + (o - wb)) & 3u;
                 uint32_t n = c;
-                if (lim != S) n = hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
+                if (lim != S && (emit_mode == 0 || WPT < 2)) n = hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
+                else if (lim != S) n = emit_mode == 3 ? hb_emit_clipped<WPT, true>(tbE64, w, lim, e, c, dst)
+                                                      : hb_emit_clipped<WPT, false>(tbEW, w, lim, e, c, dst);
                 else if (emit_mode == 0 || WPT < 2) n = hb_emit_fast<WPT>(tbE, w, e, c, dst);
                 else if constexpr (WPT >= 2) {
                     tails.push_back(emit_mode == 3 ? hb_emit_words<WPT, true>(tbE64, w, e, c, dst, mis)
