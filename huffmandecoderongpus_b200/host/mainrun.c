@@ -27,6 +27,7 @@
 #include "huffdata.h"
 
 #ifdef WITH_ORACLE_BASELINES
+#include <dlfcn.h>
 #include "huff_oracle.h"
 static void simpleDecode(struct CompressedData *cd, struct UnCompressedData *u, void *p) {
     (void)p;
@@ -168,6 +169,25 @@ int main(int argc, char *argv[]) {
     static int jumpbits = 8;
     struct decoder *simpledec = newDecoder(simpleDecode, NULL, "simpleDecode");
     struct decoder *jumptable = newDecoder(jumptableApproach, &jumpbits, "jumptableApproach");
+    /* the reference's remaining CPU approaches (framework/mainrun.c:
+     * 496-501), taken UNMODIFIED from oracle/_ref/libref.so (make -C oracle ref) when that
+     * library is present: same struct layout, same approach signature */
+    struct decoder *refdec[5] = { NULL, NULL, NULL, NULL, NULL };
+    int nref = 0;
+    {
+        const char *lib = getenv("HB_REF_LIB") ? getenv("HB_REF_LIB") : "../../oracle/_ref/libref.so";
+        void *h = dlopen(lib, RTLD_NOW | RTLD_LOCAL);
+        static const char *const names[5] = { "decodeBigtablev1", "decodeBigtableMultiSym",
+                                              "decodeBigtableSimple", "linApproach", "jumptableApproach" };
+        static const char *const labels[5] = { "ref:dbtV1", "ref:dbtMultiSym", "ref:dbtSimple",
+                                               "ref:linApproach", "ref:jumptable" };
+        for (int i = 0; h && i < 5; i++) {
+            void *f = dlsym(h, names[i]);
+            if (f) refdec[nref++] = newDecoder((void (*)(struct CompressedData *, struct UnCompressedData *, void *))f,
+                                               i >= 3 ? &jumpbits : NULL, labels[i]);
+        }
+        if (!h) fprintf(stderr, "(no %s: reference CPU approaches not listed)\n", lib);
+    }
 #endif
     const char *suite_bigtable[] = { "paper1", "hello", "news", "kjv", "book2" };   /* order of mainrun.c:558-562 */
     const char *suite_all[] = { "hello", "paper1", "news", "book2", "world192", "bible", "kjv", "ecoli" };
@@ -190,6 +210,8 @@ int main(int argc, char *argv[]) {
 #ifdef WITH_ORACLE_BASELINES
         for (int i = 0; i < ns; i++) evalandshow(simpledec, get_set(suite[i]), 1);
         for (int i = 0; i < ns; i++) evalandshow(jumptable, get_set(suite[i]), 1);
+        for (int k = 0; k < nref; k++)
+            for (int i = 0; i < ns; i++) evalandshow(refdec[k], get_set(suite[i]), 1);
 #endif
     }
     for (int i = 0; i < NSETS; i++) freeTestData(g_sets[i].td);
@@ -197,6 +219,7 @@ int main(int argc, char *argv[]) {
 #ifdef WITH_ORACLE_BASELINES
     freeDecoder(simpledec);
     freeDecoder(jumptable);
+    for (int k = 0; k < nref; k++) freeDecoder(refdec[k]);
 #endif
     return 0;
 }
