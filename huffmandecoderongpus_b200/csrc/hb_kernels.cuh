@@ -68,11 +68,22 @@ template <int WPT>
 __device__ __forceinline__ void hb_load_words(const hb_stream_args &a, uint64_t wbase,
                                               uint32_t (&w)[WPT + 1]) {
     if (wbase + WPT + 1 <= a.nwords) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(a.words + wbase);
+        if (WPT % 8 == 0 && (reinterpret_cast<uintptr_t>(a.words) & 31u) == 0) {
+            /* 32-byte aligned stream: one 256-bit load per 8 words (sm_100 LDG.256) -- a warp
+             * then touches every 128-byte line once instead of twice */
 #pragma unroll
-        for (int v = 0; v < WPT / 4; v++) {
-            uint4 q = __ldg(p + v);
-            w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+            for (int v = 0; v < WPT / 8; v++)
+                asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[8 * v]), "=r"(w[8 * v + 1]), "=r"(w[8 * v + 2]), "=r"(w[8 * v + 3]),
+                               "=r"(w[8 * v + 4]), "=r"(w[8 * v + 5]), "=r"(w[8 * v + 6]), "=r"(w[8 * v + 7])
+                             : "l"(a.words + wbase + 8 * v));
+        } else {
+            const uint4 *p = reinterpret_cast<const uint4 *>(a.words + wbase);
+#pragma unroll
+            for (int v = 0; v < WPT / 4; v++) {
+                uint4 q = __ldg(p + v);
+                w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+            }
         }
         w[WPT] = __ldg(a.words + wbase + WPT);
     } else {
@@ -427,7 +438,11 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
         }
         const uint32_t d_in = s_depth[st_in], d_out = s_depth[hb_frec_state(rec[WPT - 1])];
         uint32_t e = 0u;
-        if (d_in) e = hb_fsm_fwd(slow, __ldg(a.words + wbase - 1), w[0], d_in);   /* t > 0 here */
+        /* the word before my subsequence is my left neighbour's last one: a shuffle, and
+         * one load per warp for lane 0 */
+        uint32_t wprev = __shfl_up_sync(0xffffffffu, w[WPT - 1], 1);
+        if ((t & 31u) == 0u && d_in) wprev = __ldg(a.words + wbase - 1);
+        if (d_in) e = hb_fsm_fwd(slow, wprev, w[0], d_in);   /* t > 0 here */
         subs[(uint64_t)tile * T + t] = hb_sub_pack(e, ends - (d_in ? 1u : 0u) + (d_out ? 1u : 0u));
         if (t == T - 1) {
             s_warp[12] = hb_fsm_fwd(slow, w[WPT - 1], w[WPT], d_out);
