@@ -200,8 +200,8 @@ def main():
     ap.add_argument("--workload", default="english1g", choices=list(WORKLOADS))
     ap.add_argument("--wpt", type=int, default=0, help="words per thread (0 = library default)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words2", "words3"],
-                    help="staging stores: bytes, whole words with two / three symbols per probe, auto")
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words"],
+                    help="staging stores: bytes (hb_emit_kernel) or whole words (hb_emitw_kernel, default)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe"],
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)

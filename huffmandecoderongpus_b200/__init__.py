@@ -66,7 +66,6 @@ class LutC(C.Structure):
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
                 ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32)),
-                ("ew", C.POINTER(C.c_uint32)),
                 ("fsm_node", C.c_int32 * 256), ("node_state", C.POINTER(C.c_int32))]
 
 
@@ -218,7 +217,6 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
             "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
             "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf,)).copy(),
-            "ew": np.ctypeslib.as_array(lut.ew, shape=(1 << lut.wf,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
     finally:
@@ -274,9 +272,8 @@ class Context:
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
 
     def set_emit_path(self, path):
-        """staging stores: "bytes", "words2" / "words3" (whole words, two / three symbols per
-        probe) or "auto" (= words3)."""
-        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words2": 2, "words3": 3}[path]),
+        """staging stores: "bytes", "words" (whole 32-bit words) or "auto" (= words)."""
+        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2}[path]),
                "hb_ctx_set_emit_path")
 
     def set_sync_path(self, path):
@@ -328,9 +325,9 @@ class Codebook:
         self.maxlen, self.minlen, self.w1, self.n_entries = a.value, b.value, c.value, d.value
 
     def table(self, which):
-        """Device-resident code table copied back to the host: "lut", "stab", "etab", "e64",
-        "ew" (u32 arrays) or "fsm" (u16)."""
-        idx = {"lut": 0, "stab": 1, "etab": 2, "e64": 3, "ew": 4, "fsm": 5}[which]
+        """Device-resident code table copied back to the host: "lut", "stab", "etab", "e64"
+        (u32 arrays) or "fsm" (u16)."""
+        idx = {"lut": 0, "stab": 1, "etab": 2, "e64": 3, "fsm": 5}[which]
         buf = np.zeros(1 << 20, dtype=np.uint8)
         n = C.c_uint64()
         _check(lib().hb_codebook_download_table(self.h, idx, buf.ctypes.data, buf.size, C.byref(n)),

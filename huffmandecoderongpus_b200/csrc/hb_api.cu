@@ -185,7 +185,7 @@ extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
 }
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
-    if (!ctx || path < HB_EMIT_AUTO || path > HB_EMIT_WORDS3) return HB_ERR_ARG;
+    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS)) return HB_ERR_ARG;
     ctx->emit_path = path;
     return HB_OK;
 }
@@ -246,12 +246,12 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         cb->implied_avg_len = acc;
     }
     cudaSetDevice(ctx->device);
-    /* device layout: [single-symbol LUT][S-table][E-table][E64-table][EW-table] */
+    /* device layout: [single-symbol LUT][S-table][E-table][E64-table] */
     const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
     const size_t ns = cb->lut.fsm_states;
     /* ONE stream-ordered allocation: [tables][transducer + depth + partial steps][build
      * inputs: node array, state of every node, node of every state] */
-    const size_t lut_bytes = (sizeof(uint32_t) * (n1 + 5 * nf) + 15) & ~(size_t)15;
+    const size_t lut_bytes = (sizeof(uint32_t) * (n1 + 4 * nf) + 15) & ~(size_t)15;
     const size_t fsm_bytes = ns ? ns * 512 + 256 + 512 : 0;
     const size_t tree_bytes = sizeof(hb_node_abi) * (size_t)nodes;
     const size_t in_bytes = ((tree_bytes + 15) & ~(size_t)15) + sizeof(int32_t) * ((size_t)nodes + 256);
@@ -274,7 +274,6 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         ba.stab = cb->d_lut + n1;
         ba.etab = cb->d_lut + n1 + nf;
         ba.e64 = cb->d_lut + n1 + 2 * nf;
-        ba.ew = cb->d_lut + n1 + 4 * nf;
         ba.fsm = ns ? (uint16_t *)cb->d_fsm : nullptr;
         e = cudaMemcpyAsync(d_in, tree, tree_bytes, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && ns)
@@ -324,7 +323,6 @@ extern "C" int hb_codebook_download_table(const hb_codebook *cb, int which, void
     case HB_TABLE_S:   src = (const uint8_t *)(cb->d_lut + n1); n = 4 * nf; break;
     case HB_TABLE_E:   src = (const uint8_t *)(cb->d_lut + n1 + nf); n = 4 * nf; break;
     case HB_TABLE_E64: src = (const uint8_t *)(cb->d_lut + n1 + 2 * nf); n = 8 * nf; break;
-    case HB_TABLE_EW:  src = (const uint8_t *)(cb->d_lut + n1 + 4 * nf); n = 4 * nf; break;
     case HB_TABLE_FSM: src = cb->d_fsm; n = ns * 512; break;
     default: return HB_ERR_ARG;
     }
@@ -552,26 +550,15 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     stage_geometry(cb, WPT, &win, &stage);
     size_t smem = emit_smem_bytes(a.wf, stage);
     int grid = 1;
-    /* staging stores: whole words, three symbols per probe (measured best on both bench
-     * workloads: english1g 0.775 ms vs 0.98 with two per probe and 0.81 with byte stores);
-     * the other variants on request */
+    /* staging stores: whole words, three symbols per probe (english1g 0.75 ms vs 0.81 with
+     * byte stores); the byte-store kernel on request */
     if (ctx->emit_path != HB_EMIT_BYTES) {
-        const bool e64 = ctx->emit_path != HB_EMIT_WORDS2;
-        if (e64) {
-            ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
-            if ((rc = grid_for(ctx, hb_emitw_kernel<WPT, true>, smem, a.ntiles, &grid))) return rc;
-            hb_emitw_kernel<WPT, true><<<grid, HB_T, smem, ctx->stream>>>(
-                ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
-                (uint32_t *)(misc + 36));
-        } else {
-            ae.fast = a.fast + ((size_t)4 << a.wf);   /* EW-table */
-            if ((rc = grid_for(ctx, hb_emitw_kernel<WPT, false>, smem, a.ntiles, &grid))) return rc;
-            hb_emitw_kernel<WPT, false><<<grid, HB_T, smem, ctx->stream>>>(
-                ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
-                (uint32_t *)(misc + 36));
-        }
+        ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
+        if ((rc = grid_for(ctx, hb_emitw_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
+        hb_emitw_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
+            ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+            (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
+            (uint32_t *)(misc + 36));
     } else {
         ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
         if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;

@@ -375,42 +375,31 @@ HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], 
  *   `tail`).  No other staging byte is written by two threads.
  *   Only probes in the last word can run into the next subsequence; there the symbols
  *   pushed are clipped to the chain's count c.
- * Two table formats (hb_format.h): E64 (LDS.64, three symbols per probe: codes with
- * short codewords) and EW (LDS.32, two symbols per probe).                           */
+ * Probes read the E64-table (hb_format.h): LDS.64, up to three symbols.  A 32-bit
+ * variant with two symbols per probe was measured slower (0.98 vs 0.78 ms) and dropped. */
 struct hb_tables64 {
-    const uint32_t *fast;  /* E64- or EW-table (host emulation) */
+    const uint32_t *fast;  /* E64-table (host emulation) */
     uint32_t fast_saddr;   /* its shared-state-space address (device) */
-    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << 3 (E64) or << 2 (EW) */
+    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << 3 */
     hb_lutref slow;
 };
 
 /* one probe: symbols (first in the low byte), sh (low 5 bits = 8 * nsym; added to posk
- * as a whole), adv (low byte = bits consumed or HB_FAST_MARK; E64: bits 8+ = nsym) */
+ * as a whole), adv (low byte = bits consumed or HB_FAST_MARK, bits 8+ = nsym) */
 struct hb_pe { uint32_t syms, sh, adv; };
 
-template <bool E64>
 HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, uint32_t acc) {
     const uint32_t x = hb_funnel_r(los, his, acc) & tb.fmask;
+    uint32_t lo, hi;
+#ifdef __CUDA_ARCH__
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(x + tb.fast_saddr));
+#else
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+    lo = q[0];
+    hi = q[1];
+#endif
     hb_pe p;
-    if (E64) {
-        uint32_t lo, hi;
-#ifdef __CUDA_ARCH__
-        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(x + tb.fast_saddr));
-#else
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
-        lo = q[0];
-        hi = q[1];
-#endif
-        p.syms = lo; p.sh = hi; p.adv = hi >> 16;
-    } else {
-        uint32_t ent;
-#ifdef __CUDA_ARCH__
-        asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(x + tb.fast_saddr));
-#else
-        ent = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
-#endif
-        p.syms = ent >> 16; p.sh = ent; p.adv = ent >> 8;   /* adv bits 8+ are junk: only the position byte is used */
-    }
+    p.syms = lo; p.sh = hi; p.adv = hi >> 16;
     return p;
 }
 
@@ -454,10 +443,10 @@ HB_HD uint32_t hb_push(uint32_t syms, uint32_t sh, uint32_t &pend, uint32_t posk
 struct hb_tail { hb_out_t at; uint32_t k, bytes; };   /* k bytes (low first) to store at `at` after the barrier */
 
 /* mis: (staging address of out) & 3 */
-template <int WPT, bool E64>
+template <int WPT>
 HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
                             uint32_t c, hb_out_t out, uint32_t mis) {
-    constexpr uint32_t SC = E64 ? 3u : 2u;            /* window pre-scale: log2(bytes per entry) */
+    constexpr uint32_t SC = 3u;                       /* window pre-scale: log2(bytes per entry) */
     uint32_t acc = e, pend = 0u, posk = 8u * mis;
     hb_out_t wpp = out - mis;                         /* next staging word to store */
 #pragma unroll
@@ -468,11 +457,11 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
             /* two probes per trip: posk alternates between two registers instead of
              * being copied every probe */
             for (;;) {
-                hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                hb_pe p = hb_probe_words(tb, los, his, acc);
                 const uint32_t pk2 = hb_push(p.syms, p.sh, pend, posk, wpp);
                 acc += p.adv;
                 if (acc & 0xE0u) { posk = pk2; break; }
-                p = hb_probe_words<E64>(tb, los, his, acc);
+                p = hb_probe_words(tb, los, his, acc);
                 posk = hb_push(p.syms, p.sh, pend, pk2, wpp);
                 acc += p.adv;
                 if (acc & 0xE0u) break;
@@ -494,7 +483,7 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
         uint32_t n = (uint32_t)(wpp - out) + ((posk >> 3) & 3u);   /* symbols pushed so far */
         for (;;) {
             while (!(acc & 0xE0u)) {
-                const hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                const hb_pe p = hb_probe_words(tb, los, his, acc);
                 const uint32_t ns = (p.sh >> 3) & 3u;
                 uint32_t sh = p.sh;
                 if (n + ns > c) sh = 8u * (n < c ? c - n : 0u);
@@ -520,10 +509,10 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
 /* Partial subsequence (stream tail) in the word-store kernel: byte stores, every symbol
  * clipped to the chain's count c -- which is exactly the number of owned codeword starts,
  * so probes may run past the owned bits (into the halo or the zero padding) freely. */
-template <int WPT, bool E64>
+template <int WPT>
 HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
                                uint32_t e, uint32_t c, hb_out_t out) {
-    constexpr uint32_t SC = E64 ? 3u : 2u;
+    constexpr uint32_t SC = 3u;
     uint32_t acc = e & 0xffu, n = 0u;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
@@ -532,7 +521,7 @@ HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 
             const uint32_t los = lo << SC, his = hb_funnel_l(lo, hi, SC);
             for (;;) {
                 while (!(acc & 0xE0u)) {
-                    const hb_pe p = hb_probe_words<E64>(tb, los, his, acc);
+                    const hb_pe p = hb_probe_words(tb, los, his, acc);
                     const uint32_t ns = (p.sh >> 3) & 3u;
                     if (ns >= 1u && n < c) hb_st8(out, n, p.syms);
                     if (ns >= 2u && n + 1u < c) hb_st8(out, n + 1u, p.syms >> 8);

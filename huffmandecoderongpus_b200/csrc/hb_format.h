@@ -20,10 +20,7 @@
  *   E64-table (emit kernel, word-granular stores): two u32 per index,
  *       lo: [7:0] [15:8] [23:16] first .. third symbol (at most HB_E64_MAXSYM)
  *       hi: [4:0] = 8 * nsym (a ready-made funnel-shift amount), [23:16] B, [31:24] nsym
- *                   marker: nsym = 0, B = HB_FAST_MARK, lo = 0
- *   EW-table (same kernel, codes with longer codewords): one u32 per index,
- *       [4:0] = 8 * nsym (nsym <= 2), [7:5] = 0, [15:8] B, [23:16] first, [31:24] second symbol
- *                   marker: 0x0000E000 */
+ *                   marker: nsym = 0, B = HB_FAST_MARK, lo = 0 */
 #define HB_FAST_MARK 0xE0u
 #define HB_E_MAXSYM 2
 #define HB_E64_MAXSYM 3

@@ -223,7 +223,7 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
 /* ------------------------------------------------------------------------- */
 /* Code tables built on the device from the node array (the reference
  * has a dead precedent in framework/fastgpuOpt1.cu:22-49).  One thread per table entry:
- * entries [0, 1 << wf) are the four multi-symbol tables (same index, one walk of at most
+ * entries [0, 1 << wf) are the three multi-symbol tables (same index, one walk of at most
  * wf bits), entries after that the transducer table (state, byte).  The host only
  * validates the tree, numbers the states and builds the small single-symbol table
  * (hb_lut_build_small); csrc/hb_lut.c keeps the full host construction as the reference
@@ -233,7 +233,7 @@ struct hb_build_args {
     const int32_t *node_state;    /* state of every node, -1 for leaves */
     const int32_t *state_node;    /* node of every state */
     uint32_t nstates, wf;
-    uint32_t *stab, *etab, *e64, *ew;
+    uint32_t *stab, *etab, *e64;
     uint16_t *fsm;                /* NULL when the tree has no transducer */
 };
 
@@ -267,13 +267,11 @@ hb_build_tables_kernel(hb_build_args b) {
             b.etab[x] = HB_FAST_MARK << 16;
             b.e64[2 * x] = 0;
             b.e64[2 * x + 1] = HB_FAST_MARK << 16;
-            b.ew[x] = HB_FAST_MARK << 8;
         } else {
             const uint32_t n2 = nsym < 2u ? nsym : 2u, n3 = nsym < 3u ? nsym : 3u;
             const uint32_t s2 = syms & (n2 == 2u ? 0xffffu : 0xffu);
             b.stab[x] = sm | (used << 16) | (nsym << 24);
             b.etab[x] = s2 | (used2 << 16) | (n2 << 24);
-            b.ew[x] = (8u * n2) | (used2 << 8) | (s2 << 16);
             b.e64[2 * x] = syms;
             b.e64[2 * x + 1] = (8u * n3) | (used3 << 16) | (n3 << 24);
         }
@@ -695,17 +693,16 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 /* Emit kernel, word-granular variant (hb_emit_words): staging stores of whole 32-bit
  * words assembled in a register window, each thread's last partial word stored
  * byte-wise after a barrier; software-pipelined tile loads; bulk-store wait deferred to
- * the next window.  E64 = true: E64-table, three symbols per probe (codes with short
- * codewords); false: EW-table, two symbols per probe. */
-template <int WPT, bool E64>
-__global__ void __launch_bounds__(HB_T, (E64 ? 4 : 5))
+ * the next window.  Probes read the E64-table (three symbols per probe). */
+template <int WPT>
+__global__ void __launch_bounds__(HB_T, 4)
 hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
                uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
-    constexpr uint32_t EW = E64 ? 2u : 1u;                       /* words per table entry */
+    constexpr uint32_t EW = 2u;                                  /* words per table entry */
     __shared__ __align__(16) uint32_t s_fast[EW << HB_WF_MAX];   /* E- or E64-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_warp = smem;                               /* 16 */
@@ -722,7 +719,7 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     hb_tables64 tb64;
     tb64.fast = s_fast;
     tb64.fast_saddr = tb.fast_saddr;
-    tb64.fmask = ((1u << a.wf) - 1u) << (E64 ? 3 : 2);
+    tb64.fmask = ((1u << a.wf) - 1u) << 3;
     tb64.slow = tb.slow;
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
@@ -784,8 +781,8 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim != S) hb_emit_clipped<WPT, E64>(tb64, w, lim, e, c, dst);
-                else tl = hb_emit_words<WPT, E64>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                if (lim != S) hb_emit_clipped<WPT>(tb64, w, lim, e, c, dst);
+                else tl = hb_emit_words<WPT>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
                 if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
             }
             if (last_win && next < a.ntiles) {

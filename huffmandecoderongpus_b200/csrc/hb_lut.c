@@ -284,8 +284,7 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
     out->stab = (uint32_t *)malloc(sizeof(uint32_t) * n);
     out->etab = (uint32_t *)malloc(sizeof(uint32_t) * n);
     out->e64 = (uint32_t *)malloc(sizeof(uint32_t) * 2 * n);
-    out->ew = (uint32_t *)malloc(sizeof(uint32_t) * n);
-    if (!out->stab || !out->etab || !out->e64 || !out->ew) return HB_ERR_NOMEM;
+    if (!out->stab || !out->etab || !out->e64) return HB_ERR_NOMEM;
     for (uint32_t x = 0; x < n; x++) {
         uint32_t sm = 0, nsym = 0, used = 0;       /* unlimited symbols (S-table) */
         uint32_t e_syms = 0, e_nsym = 0, e_used = 0; /* at most HB_E_MAXSYM (E-table) */
@@ -320,9 +319,7 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
             out->etab[x] = HB_FAST_MARK << 16;
             out->e64[2 * x] = 0;
             out->e64[2 * x + 1] = HB_FAST_MARK << 16;
-            out->ew[x] = HB_FAST_MARK << 8;
         } else {
-            out->ew[x] = (8u * e_nsym) | (e_used << 8) | (e_syms << 16);
             out->e64[2 * x] = x_syms;
             out->e64[2 * x + 1] = (8u * x_nsym) | (x_used << 16) | (x_nsym << 24);
             out->stab[x] = sm | (used << 16) | (nsym << 24);
@@ -338,8 +335,7 @@ void hb_lut_free(hb_lut *lut) {
     free(lut->stab);
     free(lut->etab);
     free(lut->e64);
-    free(lut->ew);
-    lut->e64 = lut->ew = NULL;
+    lut->e64 = NULL;
     free(lut->fsm);
     free(lut->fsm_bstep);
     free(lut->node_state);

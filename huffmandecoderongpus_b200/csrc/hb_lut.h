@@ -39,7 +39,6 @@ typedef struct hb_lut {
     uint8_t   fsm_depth[256];
     uint16_t  fsm_pstep[256];
     uint32_t *e64;         /* E64-table: 2 << wf words (lo, hi interleaved) */
-    uint32_t *ew;          /* EW-table: 1 << wf words */
     /* transducer state numbering (breadth first, root = 0): node index of every state
      * and state of every node (-1 for leaves); node_state has `nodes` entries */
     int32_t   fsm_node[256];
@@ -50,7 +49,7 @@ typedef struct hb_lut {
  * first and of every deeper level (0 = defaults 11 / 10).
  * Returns 0 or a negative HB_ERR_* code (include/huffb200.h). */
 int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out);
-/* Same, without the multi-symbol tables and the transducer table (stab, etab, e64, ew,
+/* Same, without the multi-symbol tables and the transducer table (stab, etab, e64,
  * fsm stay NULL; everything else is filled): the device builds those itself
  * (hb_build_tables_kernel), the host only validates and numbers the states. */
 int hb_lut_build_small(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out);

@@ -88,15 +88,14 @@ int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
 #define HB_SYNC_PROBE 1
 int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 /* How the emit kernel fills its staging buffer:
- *   HB_EMIT_WORDS2 / HB_EMIT_WORDS3  whole 32-bit words assembled in registers, two /
- *                   three symbols per table probe (hb_emitw_kernel)
+ *   HB_EMIT_WORDS   whole 32-bit words assembled in registers, three symbols per table
+ *                   probe (hb_emitw_kernel)
  *   HB_EMIT_BYTES   byte stores, two symbols per probe (hb_emit_kernel)
- *   HB_EMIT_AUTO    WORDS3 (the fastest on every workload measured)
+ *   HB_EMIT_AUTO    = HB_EMIT_WORDS (the fastest on every workload measured)
  * Identical output; the knob exists for A/B measurement and tests. */
-#define HB_EMIT_AUTO   0
-#define HB_EMIT_BYTES  1
-#define HB_EMIT_WORDS2 2
-#define HB_EMIT_WORDS3 3
+#define HB_EMIT_AUTO  0
+#define HB_EMIT_BYTES 1
+#define HB_EMIT_WORDS 2
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
 int  hb_ctx_sync(hb_ctx *ctx);
 /* hb_decode_host cuts streams of at least two chunks into chunks of this many
@@ -130,7 +129,6 @@ void hb_codebook_destroy(hb_codebook *cb);
 #define HB_TABLE_S   1
 #define HB_TABLE_E   2
 #define HB_TABLE_E64 3
-#define HB_TABLE_EW  4
 #define HB_TABLE_FSM 5   /* byte-step transducer; 0 bytes when the tree has none */
 int  hb_codebook_download_table(const hb_codebook *cb, int which, void *dst, uint64_t capacity,
                                 uint64_t *bytes);

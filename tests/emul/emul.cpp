@@ -44,7 +44,7 @@ struct Emul {
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
     hb_tables tbS, tbE; uint32_t maxlen, minlen;
-    hb_tables64 tbE64, tbEW; int emit_mode = 0;   /* 0 byte stores (E-table), 2 / 3 word stores (EW- / E64-table) */
+    hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) */
     hb_fsm fsm; bool have_fsm = false; int sync_mode = 0;   /* 0 probe, 1 transducer on full tiles, 2 both + compare */
     uint64_t fsm_tiles = 0, fsm_mismatch = 0;
     std::vector<uint16_t> subs;
@@ -364,12 +364,10 @@ struct Emul {
                 const uint32_t mis = (al + (o - wb)) & 3u;
                 uint32_t n = c;
                 if (lim != S && (emit_mode == 0 || WPT < 2)) n = hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
-                else if (lim != S) n = emit_mode == 3 ? hb_emit_clipped<WPT, true>(tbE64, w, lim, e, c, dst)
-                                                      : hb_emit_clipped<WPT, false>(tbEW, w, lim, e, c, dst);
+                else if (lim != S) n = hb_emit_clipped<WPT>(tbE64, w, lim, e, c, dst);
                 else if (emit_mode == 0 || WPT < 2) n = hb_emit_fast<WPT>(tbE, w, e, c, dst);
                 else if constexpr (WPT >= 2) {
-                    tails.push_back(emit_mode == 3 ? hb_emit_words<WPT, true>(tbE64, w, e, c, dst, mis)
-                                                   : hb_emit_words<WPT, false>(tbEW, w, e, c, dst, mis));
+                    tails.push_back(hb_emit_words<WPT>(tbE64, w, e, c, dst, mis));
                     /* whole words inside the slice plus the tail make exactly c bytes */
                     if ((uint32_t)((tails.back().at + tails.back().k) - dst) != c) return false;
                 }
@@ -409,7 +407,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, const uint32_t *ew) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64) {
     Emul<WPT, T> E;
     E.emit_mode = emit_mode;
     E.sync_mode = sync_mode;
@@ -421,7 +419,6 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE64 = hb_tables64{e64, 0u, ((1u << wf) - 1u) << 3, slow};
-    E.tbEW = hb_tables64{ew, 0u, ((1u << wf) - 1u) << 2, slow};
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
@@ -461,13 +458,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
                         const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
-                        const uint32_t *e64, const uint32_t *ew) {
+                        const uint32_t *e64) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep, emit_mode, e64, ew)
+                          fsm_depth, fsm_pstep, emit_mode, e64)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

@@ -271,12 +271,12 @@ def test_badly_synchronising_codes(lengths, shape):
     assert rc == 0 and np.array_equal(got, syms)
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("shape", [(4, 256), (8, 256), (16, 256), (2, 8)])
 @pytest.mark.parametrize("name", ["book2", "world192"])
 def test_emit_paths(name, mode, shape):
-    """byte-store emit walk (E-table) and word-store walks (EW- / E64-table) give the same
-    bytes, at every output alignment"""
+    """byte-store emit walk (E-table) and word-store walk (E64-table) give the same bytes,
+    at every output alignment"""
     st = _stream(name)
     lut = hb.build_lut(st.tree)
     w = E.words_of(st.data, st.nbytes)

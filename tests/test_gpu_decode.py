@@ -321,7 +321,7 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words2", "words3", "bytes", "auto"):
+    for path in ("words", "bytes", "auto"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         c.set_emit_path(path)
         cb = hb.Codebook(c, f.tree)
@@ -345,7 +345,7 @@ def test_device_built_tables_match_host_construction(ctx, name):
     lut = hb.build_lut(tree)
     cb = hb.Codebook(ctx, tree)
     assert np.array_equal(cb.table("lut"), lut["entries"])
-    for key in ("stab", "etab", "e64", "ew"):
+    for key in ("stab", "etab", "e64"):
         assert np.array_equal(cb.table(key), lut[key]), key
     fsm = cb.table("fsm")
     assert fsm.size == lut["fsm_states"] * 256
