@@ -255,14 +255,24 @@ def test_sync_paths(mode, shape):
     assert rc == 0 and O.sha256(got) == O.CORPORA["news"][2]
 
 
-@pytest.mark.parametrize("lengths", [[2, 2, 2, 4, 4, 4, 4], [7] * 64 + [8] * 128, [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12],
-                                     [3, 3, 3, 3, 3, 3, 3, 3]])
-@pytest.mark.parametrize("shape", [(4, 256), (1, 4)])
+# codes whose chains merge late or never, and codes with very long codewords
+HARD_CODES = [
+    [2, 2, 2, 4, 4, 4, 4],                       # all lengths even: odd offsets never merge
+    [7] * 64 + [8] * 128,                        # nearly fixed length
+    [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12],  # minimum length 1
+    [3] * 8,                                     # exactly fixed length (closed-form path)
+    list(range(1, 31)) + [30],                   # 30-bit codewords: three table levels
+    [2] + [3] * 5 + list(range(4, 33)) + [32],   # 32-bit codewords (HB_MAX_CODELEN)
+]
+
+
+@pytest.mark.parametrize("lengths", HARD_CODES)
+@pytest.mark.parametrize("shape", [(4, 256), (8, 256), (1, 4)])
 def test_badly_synchronising_codes(lengths, shape):
-    """codes whose chains merge late or never (all-even lengths, nearly fixed length,
-    minimum length 1, exactly fixed length): many stitch rounds, unmerged hypotheses"""
+    """many stitch rounds, unmerged hypotheses, marker entries and multi-level probes"""
     tree, codes = O.tree_from_lengths(lengths)
     rng = np.random.default_rng(len(lengths))
+    # long codewords must actually occur: draw symbols uniformly, not by code probability
     syms = rng.integers(0, len(lengths), 40000 if shape[1] == 256 else 3000).astype(np.uint8)
     data, bits = O.encode_with_codes(codes, syms)
     st = O.Stream(tree, data, bits, syms.size)

@@ -300,9 +300,15 @@ def test_sync_paths_agree(dev, name, wpt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("wpt", [4, 8])
 @pytest.mark.parametrize("lengths", [[2, 2, 2, 4, 4, 4, 4], [7] * 64 + [8] * 128,
-                                     [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12], [3] * 8])
-def test_badly_synchronising_codes(ctx, dev, lengths):
+                                     [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12], [3] * 8,
+                                     list(range(1, 31)) + [30],
+                                     [2] + [3] * 5 + list(range(4, 33)) + [32]])
+def test_hard_codes(dev, lengths, wpt):
+    """chains that merge late or never; codewords of up to 32 bits (marker entries, three
+    table levels) -- symbols drawn uniformly so that the long ones occur"""
+    ctx = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
     tree, codes = O.tree_from_lengths(lengths)
     rng = np.random.default_rng(len(lengths))
     syms = rng.integers(0, len(lengths), 1 << 20).astype(np.uint8)
@@ -312,6 +318,7 @@ def test_badly_synchronising_codes(ctx, dev, lengths):
     got, res, _ = _decode_dev(ctx, cb, f, dev)
     assert res["n_symbols"] == syms.size and np.array_equal(got, syms)
     cb.close()
+    ctx.close()
 
 
 @pytest.mark.gpu
