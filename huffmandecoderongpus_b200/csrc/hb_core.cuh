@@ -384,9 +384,25 @@ struct hb_tables64 {
     hb_lutref slow;
 };
 
-/* one probe: symbols (first in the low byte), sh (low 5 bits = 8 * nsym; added to posk
- * as a whole), adv (low byte = bits consumed or HB_FAST_MARK, bits 8+ = nsym) */
-struct hb_pe { uint32_t syms, sh, adv; };
+/* one probe: symbols (first in the low byte), sel (low 16 bits: PRMT selector for the
+ * window update), inc (low 6 bits: 8 * nsym; added to posk as a whole, junk above bit 9),
+ * adv (bits consumed, or HB_E64_MARK) */
+struct hb_pe { uint32_t syms, sel, inc, adv; };
+
+HB_HD uint32_t hb_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    /* raw PRMT: only selector bits 15:0 count and every nibble used here is < 8, so the
+     * masking that __byte_perm adds is not needed */
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8u * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
 
 HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, uint32_t acc) {
     const uint32_t x = hb_funnel_r(los, his, acc) & tb.fmask;
@@ -399,9 +415,11 @@ HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, ui
     hi = q[1];
 #endif
     hb_pe p;
-    p.syms = lo; p.sh = hi; p.adv = hi >> 16;
+    p.syms = lo; p.sel = hi; p.inc = hi >> 16; p.adv = hi >> 26;
     return p;
 }
+
+HB_HD uint32_t hb_pe_nsym(const hb_pe &p) { return (p.inc >> 3) & 7u; }
 
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ void hb_st32(hb_out_t base, uint32_t idx, uint32_t v) {
@@ -418,8 +436,14 @@ HB_HD hb_pe hb_pe_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, uint32
     uint32_t sym;
     const uint32_t len = hb_probe(slow, lo, hi, pos, &sym);
     hb_pe p;
-    p.syms = sym; p.sh = 8u; p.adv = len | 0x100u;
+    p.syms = sym; p.sel = 0x4321u; p.inc = 8u; p.adv = len;
     return p;
+}
+
+/* the same probe with only its first n symbols (n < its own count) */
+HB_HD void hb_pe_clip(hb_pe &p, uint32_t n) {
+    p.sel = 0x3210u + 0x1111u * n;
+    p.inc = 8u * n;
 }
 
 /* keep a loop-invariant value in its register (the compiler otherwise recomputes the
@@ -431,11 +455,12 @@ HB_HD uint32_t hb_keep(uint32_t v) {
     return v;
 }
 
-/* shift a probe's symbols into the window; store the staging word they complete */
-HB_HD uint32_t hb_push(uint32_t syms, uint32_t sh, uint32_t &pend, uint32_t posk, hb_out_t &wpp) {
-    const uint32_t word = hb_funnel_l(pend, syms, posk);
-    const uint32_t posk_n = posk + sh;
-    pend = hb_funnel_r(pend, syms, sh);
+/* shift a probe's symbols into the window; store the staging word they complete.  At most
+ * four new bytes on top of at most three pending ones: at most one word completes. */
+HB_HD uint32_t hb_push(const hb_pe &p, uint32_t &pend, uint32_t posk, hb_out_t &wpp) {
+    const uint32_t word = hb_funnel_l(pend, p.syms, posk);   /* pending bytes below the new ones */
+    const uint32_t posk_n = posk + p.inc;
+    pend = hb_prmt(pend, p.syms, p.sel);
     if ((posk ^ posk_n) & 0x20u) { hb_st32(wpp, 0u, word); wpp += 4; }
     return posk_n;
 }
@@ -447,7 +472,7 @@ template <int WPT>
 HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
                             uint32_t c, hb_out_t out, uint32_t mis) {
     constexpr uint32_t SC = 3u;                       /* window pre-scale: log2(bytes per entry) */
-    uint32_t acc = e, pend = 0u, posk = 8u * mis;
+    uint32_t acc = e, pend = 0u, posk = 8u * mis;     /* acc: bit position in the current word */
     hb_out_t wpp = out - mis;                         /* next staging word to store */
 #pragma unroll
     for (int j = 0; j < WPT - 1; j++) {
@@ -458,20 +483,20 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
              * being copied every probe */
             for (;;) {
                 hb_pe p = hb_probe_words(tb, los, his, acc);
-                const uint32_t pk2 = hb_push(p.syms, p.sh, pend, posk, wpp);
+                const uint32_t pk2 = hb_push(p, pend, posk, wpp);
                 acc += p.adv;
                 if (acc & 0xE0u) { posk = pk2; break; }
                 p = hb_probe_words(tb, los, his, acc);
-                posk = hb_push(p.syms, p.sh, pend, pk2, wpp);
+                posk = hb_push(p, pend, pk2, wpp);
                 acc += p.adv;
                 if (acc & 0xE0u) break;
             }
-            if ((acc & 0xffu) < HB_FAST_MARK) break;
-            /* the last entry was the marker (no symbols, no count): a codeword longer
-             * than the table index starts at the position before it */
-            acc -= HB_FAST_MARK;
-            const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc & 0xffu);
-            posk = hb_push(p.syms, p.sh, pend, posk, wpp);
+            if (acc < HB_E64_MARK) break;
+            /* the last entry was the marker (no symbols): a codeword longer than the table
+             * index starts at the position before it */
+            acc -= HB_E64_MARK;
+            const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc);
+            posk = hb_push(p, pend, posk, wpp);
             acc += p.adv;
             if (acc & 0xE0u) break;
         }
@@ -483,20 +508,21 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
         uint32_t n = (uint32_t)(wpp - out) + ((posk >> 3) & 3u);   /* symbols pushed so far */
         for (;;) {
             while (!(acc & 0xE0u)) {
-                const hb_pe p = hb_probe_words(tb, los, his, acc);
-                const uint32_t ns = (p.sh >> 3) & 3u;
-                uint32_t sh = p.sh;
-                if (n + ns > c) sh = 8u * (n < c ? c - n : 0u);
-                posk = hb_push(p.syms, sh, pend, posk, wpp);
+                hb_pe p = hb_probe_words(tb, los, his, acc);
+                const uint32_t ns = hb_pe_nsym(p);
+                if (n + ns > c) hb_pe_clip(p, n < c ? c - n : 0u);
+                posk = hb_push(p, pend, posk, wpp);
                 n += ns;
                 acc += p.adv;
             }
-            if ((acc & 0xffu) < HB_FAST_MARK) break;
-            acc -= HB_FAST_MARK;
-            const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc & 0xffu);
-            posk = hb_push(p.syms, n < c ? 8u : 0u, pend, posk, wpp);
+            if (acc < HB_E64_MARK) break;
+            acc -= HB_E64_MARK;
+            hb_pe p = hb_pe_single(tb.slow, lo, hi, acc);
+            if (n >= c) hb_pe_clip(p, 0u);
+            posk = hb_push(p, pend, posk, wpp);
             n += 1u;
             acc += p.adv;
+            if (acc & 0xE0u) break;   /* a long codeword may end past HB_E64_MARK: not a marker */
         }
     }
     hb_tail tl;
@@ -513,7 +539,7 @@ template <int WPT>
 HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
                                uint32_t e, uint32_t c, hb_out_t out) {
     constexpr uint32_t SC = 3u;
-    uint32_t acc = e & 0xffu, n = 0u;
+    uint32_t acc = e, n = 0u;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
         if (32u * j < lim) {
@@ -522,19 +548,20 @@ HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 
             for (;;) {
                 while (!(acc & 0xE0u)) {
                     const hb_pe p = hb_probe_words(tb, los, his, acc);
-                    const uint32_t ns = (p.sh >> 3) & 3u;
-                    if (ns >= 1u && n < c) hb_st8(out, n, p.syms);
-                    if (ns >= 2u && n + 1u < c) hb_st8(out, n + 1u, p.syms >> 8);
-                    if (ns >= 3u && n + 2u < c) hb_st8(out, n + 2u, p.syms >> 16);
+                    const uint32_t ns = hb_pe_nsym(p);
+#pragma unroll
+                    for (uint32_t i = 0; i < HB_E64_MAXSYM; i++)
+                        if (i < ns && n + i < c) hb_st8(out, n + i, p.syms >> (8u * i));
                     n += ns;
-                    acc = (acc + p.adv) & 0xffu;
+                    acc += p.adv;
                 }
-                if (acc < HB_FAST_MARK) break;
-                acc -= HB_FAST_MARK;
+                if (acc < HB_E64_MARK) break;
+                acc -= HB_E64_MARK;
                 const hb_pe p = hb_pe_single(tb.slow, lo, hi, acc);
                 if (n < c) hb_st8(out, n, p.syms);
                 n += 1u;
-                acc = (acc + p.adv) & 0xffu;
+                acc += p.adv;
+                if (acc & 0xE0u) break;
             }
             acc -= 32u;
         }

@@ -18,12 +18,15 @@
  * the marker: nsym = 0, B = HB_FAST_MARK, low half 0; adding it pushes the
  * position byte past any legal value, which ends the probe loop.
  *   E64-table (emit kernel, word-granular stores): two u32 per index,
- *       lo: [7:0] [15:8] [23:16] first .. third symbol (at most HB_E64_MAXSYM)
- *       hi: [4:0] = 8 * nsym (a ready-made funnel-shift amount), [23:16] B, [31:24] nsym
- *                   marker: nsym = 0, B = HB_FAST_MARK, lo = 0 */
+ *       lo: first .. fourth symbol, one byte each (at most HB_E64_MAXSYM)
+ *       hi: [15:0]  PRMT selector that shifts nsym new bytes into a 4-byte window whose
+ *                   newest byte is on top: 0x3210 + 0x1111 * nsym
+ *           [21:16] 8 * nsym, [31:26] B (bits consumed)
+ *                   marker: nsym = 0 (selector 0x3210), B = HB_E64_MARK, lo = 0 */
 #define HB_FAST_MARK 0xE0u
 #define HB_E_MAXSYM 2
-#define HB_E64_MAXSYM 3
+#define HB_E64_MAXSYM 4
+#define HB_E64_MARK 48u            /* > 31 + HB_WF_MAX: a position no real probe can reach */
 #define HB_WF_MAX 12               /* widest fast-table index (16 KB per table) */
 
 /* Byte-step transducer of the sync kernel's fast path (the GPU counterpart of the

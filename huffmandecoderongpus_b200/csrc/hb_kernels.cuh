@@ -244,7 +244,7 @@ hb_build_tables_kernel(hb_build_args b) {
     if (i < nf) {
         const uint32_t x = i;
         uint32_t sm = 0, nsym = 0, used = 0, syms = 0, pos = 0;
-        uint32_t used2 = 0, used3 = 0;   /* bits used by the first two / three codewords */
+        uint32_t used2 = 0, used4 = 0;   /* bits used by the first two / four codewords */
         for (;;) {
             int32_t node = 0;
             uint32_t p = pos;
@@ -254,11 +254,11 @@ hb_build_tables_kernel(hb_build_args b) {
             }
             if (b.tree[node].izero != -1) break;      /* next codeword does not fit */
             sm |= 1u << pos;
-            if (nsym < 3u) syms |= (uint32_t)b.tree[node].sym << (8u * nsym);
+            if (nsym < 4u) syms |= (uint32_t)b.tree[node].sym << (8u * nsym);
             nsym++;
             used = p;
             if (nsym <= 2u) used2 = p;
-            if (nsym <= 3u) used3 = p;
+            if (nsym <= 4u) used4 = p;
             pos = p;
             if (pos >= b.wf) break;
         }
@@ -266,14 +266,14 @@ hb_build_tables_kernel(hb_build_args b) {
             b.stab[x] = HB_FAST_MARK << 16;
             b.etab[x] = HB_FAST_MARK << 16;
             b.e64[2 * x] = 0;
-            b.e64[2 * x + 1] = HB_FAST_MARK << 16;
+            b.e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
         } else {
-            const uint32_t n2 = nsym < 2u ? nsym : 2u, n3 = nsym < 3u ? nsym : 3u;
+            const uint32_t n2 = nsym < 2u ? nsym : 2u, n4 = nsym < 4u ? nsym : 4u;
             const uint32_t s2 = syms & (n2 == 2u ? 0xffffu : 0xffu);
             b.stab[x] = sm | (used << 16) | (nsym << 24);
             b.etab[x] = s2 | (used2 << 16) | (n2 << 24);
             b.e64[2 * x] = syms;
-            b.e64[2 * x + 1] = (8u * n3) | (used3 << 16) | (n3 << 24);
+            b.e64[2 * x + 1] = (0x3210u + 0x1111u * n4) | ((8u * n4) << 16) | (used4 << 26);
         }
         return;
     }
@@ -693,7 +693,7 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 /* Emit kernel, word-granular variant (hb_emit_words): staging stores of whole 32-bit
  * words assembled in a register window, each thread's last partial word stored
  * byte-wise after a barrier; software-pipelined tile loads; bulk-store wait deferred to
- * the next window.  Probes read the E64-table (three symbols per probe). */
+ * the next window.  Probes read the E64-table (up to four symbols per probe). */
 template <int WPT>
 __global__ void __launch_bounds__(HB_T, 4)
 hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,

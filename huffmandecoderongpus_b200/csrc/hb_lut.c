@@ -318,10 +318,10 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
             out->stab[x] = HB_FAST_MARK << 16;
             out->etab[x] = HB_FAST_MARK << 16;
             out->e64[2 * x] = 0;
-            out->e64[2 * x + 1] = HB_FAST_MARK << 16;
+            out->e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
         } else {
             out->e64[2 * x] = x_syms;
-            out->e64[2 * x + 1] = (8u * x_nsym) | (x_used << 16) | (x_nsym << 24);
+            out->e64[2 * x + 1] = (0x3210u + 0x1111u * x_nsym) | ((8u * x_nsym) << 16) | (x_used << 26);
             out->stab[x] = sm | (used << 16) | (nsym << 24);
             out->etab[x] = e_syms | (e_used << 16) | (e_nsym << 24);
         }

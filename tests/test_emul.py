@@ -298,8 +298,8 @@ def test_emit_paths(name, mode, shape):
 
 
 def test_e64_table():
-    """E64 entries against the E-/S-table semantics: up to three symbols, bits consumed,
-    8 * nsym in the low bits, marker where no codeword fits"""
+    """E64 entries against the E-/S-table semantics: up to four symbols, the window
+    selector, 8 * nsym, bits consumed, marker where no codeword fits"""
     st = _stream("world192")   # 20-bit codes: markers exist
     lut = hb.build_lut(st.tree)
     e64 = lut["e64"].reshape(-1, 2)
@@ -307,12 +307,13 @@ def test_e64_table():
     marks = 0
     for x in range(1 << lut["wf"]):
         syms, meta = int(e64[x, 0]), int(e64[x, 1])
-        ns, bits = meta >> 24, (meta >> 16) & 0xFF
+        ns, bits = (meta >> 19) & 7, meta >> 26
+        assert (meta >> 16) & 0x3FF == 8 * ns and (meta & 0xFFFF) == 0x3210 + 0x1111 * ns
         if (int(stab[x]) >> 24) == 0:
-            assert ns == 0 and bits == 0xE0 and syms == 0
+            assert ns == 0 and bits == 48 and syms == 0
             marks += 1
             continue
-        assert 1 <= ns <= 3 and (meta & 0xFFFF) == 8 * ns
+        assert 1 <= ns <= 4 and ns == min(4, int(stab[x]) >> 24)
         # walk the tree over the index bits
         node, pos, got = 0, 0, []
         while len(got) < ns:
