@@ -88,7 +88,7 @@ int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
 #define HB_SYNC_PROBE 1
 int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 /* How the emit kernel fills its staging buffer:
- *   HB_EMIT_WORDS   whole 32-bit words assembled in registers, three symbols per table
+ *   HB_EMIT_WORDS   whole 32-bit words assembled in registers, up to four symbols per table
  *                   probe (hb_emitw_kernel)
  *   HB_EMIT_BYTES   byte stores, two symbols per probe (hb_emit_kernel)
  *   HB_EMIT_AUTO    = HB_EMIT_WORDS (the fastest on every workload measured)
