@@ -1,4 +1,4 @@
-mkdir -p gpurun_out/r01b; O=gpurun_out/r01b
+mkdir -p gpurun_out/r01c; O=gpurun_out/r01c
 python bench.py > $O/bench_default.log 2>&1; tail -1 $O/bench_default.log | cut -c1-300
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.log 2>&1
 python bench.py --workload fib4g --steps 20 --warmup 3 --no-cpu > $O/bench_fib4g.log 2>&1
