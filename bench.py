@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words"],
                     help="staging stores: bytes (hb_emit_kernel) or whole words (hb_emitw_kernel, default)")
-    ap.add_argument("--sync-path", default="auto", choices=["auto", "probe"],
+    ap.add_argument("--sync-path", default="auto", choices=["auto", "probe", "fsm"],
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -326,7 +326,7 @@ def main():
     b_alg = comp_bytes_own + n_mine                 # compressed read once + decoded written once
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
-    sync_name = "hb_fsm_sync_kernel" if args.sync_path == "auto" else "hb_sync_kernel"
+    sync_name = "hb_sync_kernel" if args.sync_path == "probe" else "hb_fsm_sync_kernel"
     emit_name = "hb_emit_kernel" if args.emit_path == "bytes" else "hb_emitw_kernel"
     dom_name = {"sync": sync_name, "emit": emit_name}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9

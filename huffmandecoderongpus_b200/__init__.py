@@ -105,6 +105,7 @@ def lib():
     L.hb_ctx_destroy.restype = None
     L.hb_ctx_configure.argtypes = [vp, i32, i32]
     L.hb_ctx_set_sync_path.argtypes = [vp, i32]
+    L.hb_ctx_set_phase_timing.argtypes = [vp, i32]
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_sync.argtypes = [vp]
@@ -271,14 +272,21 @@ class Context:
     def configure(self, words_per_thread=0, ctas_per_sm=0):
         _check(lib().hb_ctx_configure(self.h, words_per_thread, ctas_per_sm), "hb_ctx_configure")
 
+    def set_phase_timing(self, mode):
+        """"auto", "always" or "never": whether decodes record the per-phase events."""
+        _check(lib().hb_ctx_set_phase_timing(self.h, {"auto": 0, "always": 1, "never": 2}[mode]),
+               "hb_ctx_set_phase_timing")
+
     def set_emit_path(self, path):
         """staging stores: "bytes", "words" (whole 32-bit words) or "auto" (= words)."""
         _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2}[path]),
                "hb_ctx_set_emit_path")
 
     def set_sync_path(self, path):
-        """"auto" (transducer sync kernel on full tiles when the code has one) or "probe"."""
-        _check(lib().hb_ctx_set_sync_path(self.h, {"auto": 0, "probe": 1}[path]), "hb_ctx_set_sync_path")
+        """"auto" (transducer sync kernel for streams of two waves of tiles or more), "probe"
+        (probe kernel only) or "fsm" (transducer kernel whenever the code has one)."""
+        _check(lib().hb_ctx_set_sync_path(self.h, {"auto": 0, "probe": 1, "fsm": 2}[path]),
+               "hb_ctx_set_sync_path")
 
     def set_host_chunk(self, nbytes):
         _check(lib().hb_ctx_set_host_chunk(self.h, nbytes), "hb_ctx_set_host_chunk")

@@ -36,6 +36,9 @@ struct hb_ctx {
     int ctas_per_sm = 0;
     int sync_path = HB_SYNC_AUTO;
     int emit_path = HB_EMIT_AUTO;
+    int phase_timing = HB_PHASES_AUTO;
+    bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
+    bool map_fused = false;       /* the last hb_shard_map left up/top to hb_scan_small_kernel */
     uint32_t last_launches = 0;   /* kernels launched by the last map + emit pair */
     cudaEvent_t ev0[HB_NEV];   /* default event set */
     cudaEvent_t *ev = nullptr; /* set used by the current step */
@@ -179,8 +182,14 @@ extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_
 }
 
 extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
-    if (!ctx || (path != HB_SYNC_AUTO && path != HB_SYNC_PROBE)) return HB_ERR_ARG;
+    if (!ctx || path < HB_SYNC_AUTO || path > HB_SYNC_FSM) return HB_ERR_ARG;
     ctx->sync_path = path;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_set_phase_timing(hb_ctx *ctx, int mode) {
+    if (!ctx || mode < HB_PHASES_AUTO || mode > HB_PHASES_NEVER) return HB_ERR_ARG;
+    ctx->phase_timing = mode;
     return HB_OK;
 }
 
@@ -418,6 +427,16 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
 
 static uint64_t *misc_words(hb_ctx *ctx) { return (uint64_t *)ctx->misc.p; }
 
+/* The three inner events (sync | scan | emit boundaries) cost ~4 us each: a third of the
+ * device time of a decode of the shipped corpora.  They are recorded for streams of more
+ * than one scan CTA's worth of tiles, while a timing ring is armed (bench), or on request;
+ * otherwise hb_result reports ms_total only. */
+static bool phase_events(const hb_ctx *ctx, uint32_t ntiles) {
+    if (ctx->phase_timing == HB_PHASES_ALWAYS) return true;
+    if (ctx->phase_timing == HB_PHASES_NEVER) return false;
+    return ntiles > 1024u || (ctx->tim_ev && ctx->ev != ctx->ev0);
+}
+
 /* Transducer sync kernel over tiles [0, n_full).  G groups of HB_T threads share one
  * table copy per CTA; G is chosen for the most resident warps per SM. */
 template <int WPT, int G>
@@ -488,11 +507,16 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     ctx->last_launches = 0;
     uint32_t tile0 = 0;
-    if (ctx->sync_path == HB_SYNC_AUTO && cb->d_fsm && a.minlen != a.maxlen) {
-        /* full tiles: byte-step transducer kernel */
+    if (ctx->sync_path != HB_SYNC_PROBE && cb->d_fsm && a.minlen != a.maxlen) {
+        /* full tiles: byte-step transducer kernel -- from two waves of tiles on; below
+         * that one probe-kernel launch for everything is quicker */
         const uint32_t n_full = (uint32_t)(a.bits_own / ((uint64_t)HB_T * 32u * WPT));
-        if (n_full && (rc = launch_fsm_sync<WPT>(ctx, cb, a, n_full))) return rc;
-        tile0 = n_full;
+        const uint32_t min_tiles = ctx->sync_path == HB_SYNC_FSM ? 1u
+                                 : 2u * HB_SYNC_MIN_CTAS * (uint32_t)ctx->prop.multiProcessorCount;
+        if (n_full >= min_tiles) {
+            if ((rc = launch_fsm_sync<WPT>(ctx, cb, a, n_full))) return rc;
+            tile0 = n_full;
+        }
     }
     if (tile0 < a.ntiles) {
         size_t smem = sync_smem_bytes<WPT>(a.wf);
@@ -503,19 +527,22 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
         CK(cudaGetLastError());
         ctx->last_launches++;
     }
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    hb_scan_up_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>((const uint32_t *)ctx->tmaps.p, a.ntiles,
-                                                          (uint64_t *)ctx->wmaps.p,
-                                                          (uint64_t *)ctx->cmaps.p);
-    CK(cudaGetLastError());
-    hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
-                                                  (uint64_t *)ctx->cprefix.p, misc_words(ctx));
-    CK(cudaGetLastError());
-    ctx->last_launches += 2;
+    if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->map_fused = ctx->fuse_small && ncta == 1 && !d_map;
+    if (!ctx->map_fused) {
+        hb_scan_up_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>((const uint32_t *)ctx->tmaps.p, a.ntiles,
+                                                              (uint64_t *)ctx->wmaps.p,
+                                                              (uint64_t *)ctx->cmaps.p);
+        CK(cudaGetLastError());
+        hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
+                                                      (uint64_t *)ctx->cprefix.p, misc_words(ctx));
+        CK(cudaGetLastError());
+        ctx->last_launches += 2;
+    }
     if (d_map)
         CK(cudaMemcpyAsync(d_map, misc_words(ctx), 32 * sizeof(uint64_t), cudaMemcpyDeviceToDevice,
                            ctx->stream));
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->have_map = true;
     ctx->map_ntiles = a.ntiles;
     ctx->map_ncta = ncta;
@@ -529,13 +556,28 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     const uint32_t ncta = ctx->map_ncta;
     uint64_t *misc = misc_words(ctx);
     int rc;
-    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    hb_scan_down_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
-        (const uint32_t *)ctx->tmaps.p, a.ntiles, (const uint64_t *)ctx->wmaps.p,
-        (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
-        (uint64_t *)ctx->tile_base.p, misc + 32, a.bits_own, a.bits_avail);
-    CK(cudaGetLastError());
-    {   /* re-chain the head of every tile whose true entry offset is not 0 (S-table) */
+    if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    uint32_t scan_launches = 2;
+    if (ctx->map_fused) {
+        /* small single-shard stream: up, top, down and fix in one launch */
+        hb_scan_small_kernel<WPT><<<1, HB_SCAN_T, 0, ctx->stream>>>(
+            a, (const uint32_t *)ctx->tmaps.p, d_entry_base, misc, (uint8_t *)ctx->tile_entry.p,
+            (uint64_t *)ctx->tile_base.p, misc + 32, (uint16_t *)ctx->subs.p);
+        CK(cudaGetLastError());
+        scan_launches = 1;
+        if (a.minlen == a.maxlen) {
+            hb_fix_fixed_kernel<WPT><<<a.ntiles, HB_T, 0, ctx->stream>>>(
+                a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
+            CK(cudaGetLastError());
+            scan_launches = 2;
+        }
+    } else {
+        hb_scan_down_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
+            (const uint32_t *)ctx->tmaps.p, a.ntiles, (const uint64_t *)ctx->wmaps.p,
+            (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
+            (uint64_t *)ctx->tile_base.p, misc + 32, a.bits_own, a.bits_avail);
+        CK(cudaGetLastError());
+        /* re-chain the head of every tile whose true entry offset is not 0 (S-table) */
         if (a.minlen == a.maxlen)
             hb_fix_fixed_kernel<WPT><<<a.ntiles, HB_T, 0, ctx->stream>>>(
                 a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
@@ -544,7 +586,8 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
                 a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->last_launches += scan_launches + 1;   /* + the emit kernel below */
+    if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     hb_stream_args ae = a;
     uint32_t win = 0, stage = 0;
     stage_geometry(cb, WPT, &win, &stage);
@@ -637,12 +680,14 @@ static int finish_result(hb_ctx *ctx, uint32_t ntiles, uint32_t launches, hb_res
     res->launches = launches;
     res->tiles = ntiles;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) res->ms_sync = ms;
-    float s1 = 0, s2 = 0;
-    cudaEventElapsedTime(&s1, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&s2, ctx->ev[2], ctx->ev[3]);
-    res->ms_scan = s1 + s2;
-    if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) res->ms_emit = ms;
+    if (phase_events(ctx, ntiles)) {
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) res->ms_sync = ms;
+        float s1 = 0, s2 = 0;
+        cudaEventElapsedTime(&s1, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&s2, ctx->ev[2], ctx->ev[3]);
+        res->ms_scan = s1 + s2;
+        if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) res->ms_emit = ms;
+    }
     if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]) == cudaSuccess) res->ms_total = ms;
     cudaGetLastError();
     if ((uint32_t)ctx->h_res[4] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
@@ -684,7 +729,7 @@ extern "C" int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_c
     default: rc = HB_ERR_ARG;
     }
     if (rc) return rc;
-    launches = ctx->last_launches + 3;   /* + scan down, fix, emit */
+    launches = ctx->last_launches;
     if (res) return finish_result(ctx, a.ntiles, launches, res);
     return HB_OK;
 }
@@ -694,7 +739,10 @@ extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *
                                 uint64_t out_capacity, hb_result *res) {
     hb_result local;
     if (!res) res = &local;
+    if (!ctx) return HB_ERR_ARG;
+    ctx->fuse_small = true;    /* nobody reads the shard map between the two phases */
     int rc = hb_shard_map(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr);
+    ctx->fuse_small = false;
     if (rc) return rc;
     return hb_shard_emit(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr, d_out, out_capacity, res);
 }
@@ -784,7 +832,7 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
         CK(cudaEventRecord(ctx->pipe_ev[2 * k + 1], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 * k + 1], 0));
         if (n) CK(cudaMemcpyAsync(out + base, d_out + base, n, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        launches += ctx->last_launches + 3;
+        launches += ctx->last_launches;
         tiles += ctx->map_ntiles;
         base += n;
         cur = (uint32_t)(m & 31u);

@@ -667,6 +667,109 @@ hb_fix_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry, uint16_t
     hb_fix_entries<WPT, T>(tb, word, subs + (uint64_t)tile * T, tile_lim, E);
 }
 
+/* ------------------------------------------------------------------------- */
+/* Small streams (at most 1024 tiles = one scan CTA, single shard): hb_scan_up, _top,
+ * _down and hb_fix in ONE launch.  The shipped corpora are a few hundred tiles; for
+ * them four dependent tiny kernels cost more than the sync and emit kernels together
+ * (tools/latency_probe.py).  Same results in the same buffers; the tile maps stay in
+ * registers between the up and the down sweep. */
+template <int WPT>
+__global__ void __launch_bounds__(HB_SCAN_T)
+hb_scan_small_kernel(hb_stream_args a, const uint32_t *__restrict__ tmaps,
+                     const uint64_t *__restrict__ entry_base, uint64_t *__restrict__ shard_map,
+                     uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
+                     uint64_t *__restrict__ result, uint16_t *__restrict__ subs) {
+    constexpr int T = HB_T;
+    constexpr uint32_t TS = T * 32u * WPT;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* S-table, for the fix step */
+    __shared__ uint64_t s_w[32][32];
+    __shared__ uint32_t s_we[32];
+    __shared__ uint64_t s_wb[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool fixed_len = a.minlen == a.maxlen;
+    if (!fixed_len)
+        for (uint32_t i = threadIdx.x; i < (1u << a.wf); i += HB_SCAN_T) s_fast[i] = __ldg(a.fast + i);
+
+    /* up: the composition of this warp's 32 tile maps, all 32 hypotheses at once */
+    uint32_t reg[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t tile = (uint32_t)wid * 32u + j;
+        reg[j] = tile < a.ntiles ? __ldg(tmaps + (uint64_t)tile * 32 + lane) : hb_map_pack32(lane, 0);
+    }
+    {
+        uint32_t cur = lane, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t m = __shfl_sync(0xffffffffu, reg[j], cur);
+            cnt += m >> 8;
+            cur = m & 31u;
+        }
+        s_w[wid][lane] = hb_map_pack64(cur, cnt);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        /* top: the shard's map (kept for hb_result); down over the warp maps from the
+         * shard's entry offset */
+        uint32_t c2 = lane;
+        uint64_t n2 = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint64_t m = s_w[j][c2];
+            n2 += m >> 8;
+            c2 = (uint32_t)m & 31u;
+        }
+        shard_map[lane] = hb_map_pack64(c2, n2);
+        const uint32_t E = entry_base ? (uint32_t)entry_base[0] & 31u : 0u;
+        const uint64_t B = entry_base ? entry_base[1] : 0ull;
+        uint32_t cur = E;
+        uint64_t b = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            if (lane == j) { s_we[j] = cur; s_wb[j] = b; }
+            const uint64_t m = s_w[j][cur];
+            b += m >> 8;
+            cur = (uint32_t)m & 31u;
+        }
+        if (lane == 0) {
+            /* a last codeword that runs past the end of the data is not a symbol */
+            uint64_t total = b;
+            if (total && a.bits_own + cur > a.bits_avail) total--;
+            result[0] = total;
+            result[1] = cur;
+            result[2] = E;
+            result[3] = B;
+        }
+    }
+    __syncthreads();
+    /* down inside the warp; lane j keeps tile j's entry offset and output base */
+    uint32_t cur = s_we[wid], my_e = 0;
+    uint64_t b = s_wb[wid], my_b = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (lane == j) { my_e = cur; my_b = b; }
+        const uint32_t m = __shfl_sync(0xffffffffu, reg[j], cur);
+        b += m >> 8;
+        cur = m & 31u;
+    }
+    const uint32_t tile = (uint32_t)wid * 32u + lane;
+    if (tile >= a.ntiles) return;
+    tile_entry[tile] = (uint8_t)my_e;
+    tile_base[tile] = my_b;
+    /* fix: re-chain the head of a tile whose true entry offset is not the recorded 0
+     * (fixed-length codes: hb_fix_fixed_kernel, launched by the host) */
+    if (my_e == 0 || fixed_len) return;
+    hb_tables tb;
+    tb.fast = s_fast;
+    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    const uint64_t own_left = a.bits_own - (uint64_t)tile * TS;
+    const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
+    hb_tile_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
+    hb_fix_entries<WPT, T>(tb, word, subs + (uint64_t)tile * T, tile_lim, my_e);
+}
+
 /* Fixed-length codes: the chain of the tile's true entry offset never meets the
  * recorded one, but every subsequence's (entry, count) follows arithmetically.
  * One thread per subsequence. */

@@ -79,13 +79,18 @@ const char *hb_last_error(const hb_ctx *ctx);
 /* words_per_thread: 4, 8 or 16 32-bit words per subsequence (0 = default);
  * ctas_per_sm: persistent CTAs per SM (0 = occupancy-derived). */
 int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
-/* Which sync kernel resolves the chains of full tiles: HB_SYNC_AUTO picks the
- * byte-step transducer kernel whenever the code table has one (every tree with at
- * most 256 internal nodes that is not a fixed-length code), HB_SYNC_PROBE forces the
- * multi-symbol probe kernel (the only path for other trees and for partial tiles).
- * Both produce identical records; the knob exists for A/B measurement and tests. */
+/* Which sync kernel resolves the chains of full tiles.  The byte-step transducer kernel
+ * needs a code table with a transducer (every tree with at most 256 internal nodes that
+ * is not a fixed-length code); the multi-symbol probe kernel handles everything,
+ * including the partial tile at the end of a shard.
+ *   HB_SYNC_AUTO   transducer kernel for streams of at least two waves of tiles, one
+ *                  probe-kernel launch for smaller ones (a second launch and a second
+ *                  table load cost more than they save there)
+ *   HB_SYNC_PROBE  probe kernel only        HB_SYNC_FSM  transducer kernel whenever possible
+ * Identical records either way; the knob exists for A/B measurement and tests. */
 #define HB_SYNC_AUTO  0
 #define HB_SYNC_PROBE 1
+#define HB_SYNC_FSM   2
 int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 /* How the emit kernel fills its staging buffer:
  *   HB_EMIT_WORDS   whole 32-bit words assembled in registers, up to four symbols per table
@@ -97,6 +102,13 @@ int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 #define HB_EMIT_BYTES 1
 #define HB_EMIT_WORDS 2
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
+/* hb_result's per-phase times need three extra CUDA events per decode (~4 us each).
+ * HB_PHASES_AUTO records them for streams of more than 1024 tiles and while a timing ring
+ * is armed (hb_ctx_timing_begin); smaller decodes then report ms_total only. */
+#define HB_PHASES_AUTO   0
+#define HB_PHASES_ALWAYS 1
+#define HB_PHASES_NEVER  2
+int  hb_ctx_set_phase_timing(hb_ctx *ctx, int mode);
 int  hb_ctx_sync(hb_ctx *ctx);
 /* hb_decode_host cuts streams of at least two chunks into chunks of this many
  * compressed bytes (rounded to whole tiles) and overlaps upload, decode and

@@ -38,6 +38,7 @@ def run(name, tree, data, bits, syms, ctx, dev):
 def main():
     dev = torch.device("cuda:0")
     ctx = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    ctx.set_phase_timing("always")
     rng = np.random.default_rng(1)
     n = 1 << 24
     for name, lengths in (("even", [2, 2, 2, 4, 4, 4, 4]), ("7or8", [7] * 64 + [8] * 128)):
