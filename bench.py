@@ -206,6 +206,8 @@ def main():
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--host-chunk-mib", type=int, default=0,
+                    help="chunk size of the pipelined host path in MiB (0 = library default, 32)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -238,6 +240,8 @@ def main():
     ctx = hb.Context(local, stream=torch.cuda.current_stream().cuda_stream,
                      words_per_thread=args.wpt, ctas_per_sm=args.ctas_per_sm)
     ctx.set_sync_path(args.sync_path)
+    if args.host_chunk_mib:
+        ctx.set_host_chunk(args.host_chunk_mib << 20)
     ctx.set_emit_path(args.emit_path)
     model = hb.Model(kind)
     cb = hb.Codebook(ctx, model.tree)

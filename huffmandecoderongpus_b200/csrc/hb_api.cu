@@ -239,7 +239,6 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
     if (rc != HB_OK) { delete cb; return rc; }
     {   /* expected code length under the code's own implied distribution */
         double acc = 0.0;
-        for (int i = 0; i < 256; i++) (void)i;
         /* iterative DFS over the (validated) tree, depth kept alongside */
         int32_t st_node[2 * 64 + 4];
         int st_depth[2 * 64 + 4];
