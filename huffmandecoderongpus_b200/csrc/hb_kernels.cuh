@@ -897,6 +897,9 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             /* every word store is done: the last, partial word of each slice (its other
              * lanes belong to the right neighbour, who has just overwritten them) */
             hb_store_tail(tl);
+            /* every thread orders its own staging writes before the async proxy (the bulk
+             * store below reads them), then the barrier orders the threads */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             uint32_t hi_b = *s_hi;
             if (hi_b > nvalid) hi_b = nvalid;
@@ -1003,6 +1006,7 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                 else hb_emit_slow<WPT>(tb.slow, w, lim, e, c, dst);
                 if (o + c - wb >= win && o + c < nk) s_warp[15] = o + c;   /* I am the window's last thread */
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* my staging writes -> async proxy */
             __syncthreads();
             uint32_t hi_b = s_warp[15];
             if (hi_b > nvalid) hi_b = nvalid;
