@@ -309,3 +309,17 @@ def encode_with_codes(codes, syms):
         bits[pos[m] + k] = table[syms[m], k]
     data = np.packbits(bits, bitorder="little")
     return np.concatenate([data, np.zeros(32, np.uint8)]), total
+
+
+def random_lengths(rng, nleaves, maxlen):
+    """code lengths of a random complete binary tree with nleaves leaves, depth <= maxlen"""
+    lens = [1, 1]
+    while len(lens) < nleaves:
+        cand = [i for i, l in enumerate(lens) if l < maxlen]
+        if not cand:
+            break
+        # favour deep leaves now and then so that long codewords appear
+        i = cand[int(rng.integers(len(cand)))] if rng.random() < 0.7 else max(cand, key=lambda k: lens[k])
+        l = lens.pop(i) + 1
+        lens += [l, l]
+    return lens

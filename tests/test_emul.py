@@ -341,3 +341,32 @@ def test_tree_with_more_than_256_internal_nodes(shape):
     assert np.array_equal(O.simple_decode(st), want)
     got, stats, rc = E.decode(st, *shape, lut=lut)
     assert rc == 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_codes_and_streams(seed):
+    """the CPU twin of tests/test_gpu_stress.py: random complete trees (codewords of up to 32
+    bits), random streams, every tile shape and both emit walks, against the oracle"""
+    rng = np.random.default_rng(2000 + seed)
+    for case in range(12):
+        nleaves = int(rng.choice([2, 3, 5, 17, 64, 200, 256]))
+        maxlen = int(rng.choice([4, 9, 13, 20, 32]))
+        lengths = O.random_lengths(rng, nleaves, maxlen)
+        tree, codes = O.tree_from_lengths(lengths)
+        w = np.array([2.0 ** (-l) for l in lengths])
+        mode = int(rng.integers(3))
+        p = np.ones(len(lengths)) if mode == 0 else (w if mode == 1 else 1.0 / w)
+        n = int(rng.choice([1, 7, 300, 5000, 40000]))
+        syms = rng.choice(len(lengths), size=n, p=p / p.sum())
+        data, bits = O.encode_with_codes(codes, syms)
+        st = O.Stream(tree, data, bits, n)
+        want = (syms & 255).astype(np.uint8)
+        shape = [(4, 256), (8, 256), (16, 256), (2, 8), (1, 4)][int(rng.integers(5))]
+        lut = hb.build_lut(tree)
+        wds = E.words_of(st.data, (bits + 7) // 8)
+        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=int(rng.integers(2)),
+                                   out_offset=int(rng.integers(16)))
+        tag = (seed, case, nleaves, maxlen, n, shape)
+        assert rc == 0 and int(res[0]) == n, tag
+        assert np.array_equal(out[:n], want), tag
+        assert not out[n:].any(), tag
