@@ -66,7 +66,8 @@ class LutC(C.Structure):
                 ("fsm_states", C.c_uint32), ("fsm", C.POINTER(C.c_uint16)),
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
                 ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32)),
-                ("fsm_node", C.c_int32 * 256), ("node_state", C.POINTER(C.c_int32))]
+                ("fsm_node", C.c_int32 * 256), ("node_state", C.POINTER(C.c_int32)),
+                ("wf64", C.c_uint32), ("implied_avg_len", C.c_double)]
 
 
 class RefCompressedData(C.Structure):
@@ -217,7 +218,8 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "wf": lut.wf,
             "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
             "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
-            "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf,)).copy(),
+            "wf64": lut.wf64, "implied_avg_len": lut.implied_avg_len,
+            "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf64,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
     finally:

@@ -237,22 +237,7 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
      * multi-symbol tables and the transducer table are built on the device */
     int rc = hb_lut_build_small(tree, nodes, 0, 0, &cb->lut);
     if (rc != HB_OK) { delete cb; return rc; }
-    {   /* expected code length under the code's own implied distribution */
-        double acc = 0.0;
-        /* iterative DFS over the (validated) tree, depth kept alongside */
-        int32_t st_node[2 * 64 + 4];
-        int st_depth[2 * 64 + 4];
-        int sp = 0;
-        st_node[0] = 0; st_depth[0] = 0; sp = 1;
-        while (sp > 0) {
-            const int v = st_node[--sp];
-            const int d = st_depth[sp];
-            if (tree[v].izero == -1) { acc += (double)d / (double)(1ull << d); continue; }
-            st_node[sp] = tree[v].izero; st_depth[sp++] = d + 1;
-            st_node[sp] = tree[v].ione;  st_depth[sp++] = d + 1;
-        }
-        cb->implied_avg_len = acc;
-    }
+    cb->implied_avg_len = cb->lut.implied_avg_len;
     cudaSetDevice(ctx->device);
     /* device layout: [single-symbol LUT][S-table][E-table][E64-table] */
     const size_t n1 = cb->lut.n_entries, nf = (size_t)1 << cb->lut.wf;
@@ -279,6 +264,7 @@ extern "C" int hb_codebook_create(hb_ctx *ctx, const hb_node_abi *tree, int node
         ba.state_node = d_ns + nodes;
         ba.nstates = (uint32_t)ns;
         ba.wf = cb->lut.wf;
+        ba.wf64 = cb->lut.wf64;
         ba.stab = cb->d_lut + n1;
         ba.etab = cb->d_lut + n1 + nf;
         ba.e64 = cb->d_lut + n1 + 2 * nf;
@@ -330,7 +316,7 @@ extern "C" int hb_codebook_download_table(const hb_codebook *cb, int which, void
     case HB_TABLE_LUT: src = (const uint8_t *)cb->d_lut; n = 4 * n1; break;
     case HB_TABLE_S:   src = (const uint8_t *)(cb->d_lut + n1); n = 4 * nf; break;
     case HB_TABLE_E:   src = (const uint8_t *)(cb->d_lut + n1 + nf); n = 4 * nf; break;
-    case HB_TABLE_E64: src = (const uint8_t *)(cb->d_lut + n1 + 2 * nf); n = 8 * nf; break;
+    case HB_TABLE_E64: src = (const uint8_t *)(cb->d_lut + n1 + 2 * nf); n = (size_t)8 << cb->lut.wf64; break;
     case HB_TABLE_FSM: src = cb->d_fsm; n = ns * 512; break;
     default: return HB_ERR_ARG;
     }
@@ -596,6 +582,8 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
      * byte stores); the byte-store kernel on request */
     if (ctx->emit_path != HB_EMIT_BYTES) {
         ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
+        ae.wf = cb->lut.wf64;                     /* ... and its own index width */
+        smem += (size_t)8 << ae.wf;               /* the table sits in front of the staging buffer */
         if ((rc = grid_for(ctx, hb_emitw_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
         hb_emitw_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
             ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,

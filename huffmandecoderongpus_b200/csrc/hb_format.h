@@ -17,7 +17,10 @@
  * When not even the first codeword fits (code longer than wf bits) the entry is
  * the marker: nsym = 0, B = HB_FAST_MARK, low half 0; adding it pushes the
  * position byte past any legal value, which ends the probe loop.
- *   E64-table (emit kernel, word-granular stores): two u32 per index,
+ *   E64-table (emit kernel, word-granular stores), indexed by the next wf64 <= wf bits
+ *   (wf64 = 11 when the code's implied mean codeword length is at most 3.5 bits: four
+ *   codewords then usually fit and the table takes half the shared memory -- else 12):
+ *   two u32 per index,
  *       lo: first .. fourth symbol, one byte each (at most HB_E64_MAXSYM)
  *       hi: [15:0]  PRMT selector that shifts nsym new bytes into a 4-byte window whose
  *                   newest byte is on top: 0x3210 + 0x1111 * nsym

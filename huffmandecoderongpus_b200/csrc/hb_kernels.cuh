@@ -232,7 +232,7 @@ struct hb_build_args {
     const hb_node_abi *tree;      /* reference node array, 12-byte structs */
     const int32_t *node_state;    /* state of every node, -1 for leaves */
     const int32_t *state_node;    /* node of every state */
-    uint32_t nstates, wf;
+    uint32_t nstates, wf, wf64;   /* wf64 <= wf: index width of the E64-table */
     uint32_t *stab, *etab, *e64;
     uint16_t *fsm;                /* NULL when the tree has no transducer */
 };
@@ -244,7 +244,7 @@ hb_build_tables_kernel(hb_build_args b) {
     if (i < nf) {
         const uint32_t x = i;
         uint32_t sm = 0, nsym = 0, used = 0, syms = 0, pos = 0;
-        uint32_t used2 = 0, used4 = 0;   /* bits used by the first two / four codewords */
+        uint32_t used2 = 0, used4 = 0, n4 = 0;   /* bits used by the first two codewords / by the first (at most four) that end within wf64 bits */
         for (;;) {
             int32_t node = 0;
             uint32_t p = pos;
@@ -258,22 +258,27 @@ hb_build_tables_kernel(hb_build_args b) {
             nsym++;
             used = p;
             if (nsym <= 2u) used2 = p;
-            if (nsym <= 4u) used4 = p;
+            if (nsym <= 4u && p <= b.wf64) { used4 = p; n4 = nsym; }
             pos = p;
             if (pos >= b.wf) break;
         }
         if (nsym == 0) {
             b.stab[x] = HB_FAST_MARK << 16;
             b.etab[x] = HB_FAST_MARK << 16;
-            b.e64[2 * x] = 0;
-            b.e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
         } else {
-            const uint32_t n2 = nsym < 2u ? nsym : 2u, n4 = nsym < 4u ? nsym : 4u;
+            const uint32_t n2 = nsym < 2u ? nsym : 2u;
             const uint32_t s2 = syms & (n2 == 2u ? 0xffffu : 0xffu);
             b.stab[x] = sm | (used << 16) | (nsym << 24);
             b.etab[x] = s2 | (used2 << 16) | (n2 << 24);
-            b.e64[2 * x] = syms;
-            b.e64[2 * x + 1] = (0x3210u + 0x1111u * n4) | ((8u * n4) << 16) | (used4 << 26);
+        }
+        if (x < (1u << b.wf64)) {
+            if (n4 == 0) {
+                b.e64[2 * x] = 0;
+                b.e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
+            } else {
+                b.e64[2 * x] = n4 == 4u ? syms : (syms & ((1u << (8u * n4)) - 1u));
+                b.e64[2 * x + 1] = (0x3210u + 0x1111u * n4) | ((8u * n4) << 16) | (used4 << 26);
+            }
         }
         return;
     }
@@ -806,9 +811,9 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
     constexpr uint32_t EW = 2u;                                  /* words per table entry */
-    __shared__ __align__(16) uint32_t s_fast[EW << HB_WF_MAX];   /* E- or E64-table (static: constant address) */
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_warp = smem;                               /* 16 */
+    uint32_t *s_fast = smem;                               /* E64-table: 2 << a.wf words (a.wf = its own width) */
+    uint32_t *s_warp = smem + (EW << a.wf);                /* 16 */
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
     const int t = threadIdx.x;
 

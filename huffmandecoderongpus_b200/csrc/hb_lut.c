@@ -195,6 +195,24 @@ static int lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_
     memset(have, 0, sizeof(have));
     collect_codes(tree, 0, 0, 0, out, have);
     out->wf = HB_WF_MAX;
+    {   /* mean codeword length under the code's own implied distribution (iterative DFS) */
+        double acc = 0.0;
+        int32_t st_node[2 * HB_MAX_CODELEN + 4];
+        int st_depth[2 * HB_MAX_CODELEN + 4];
+        int sp = 1;
+        st_node[0] = 0; st_depth[0] = 0;
+        while (sp > 0) {
+            const int32_t v = st_node[--sp];
+            const int d = st_depth[sp];
+            if (is_leaf(&tree[v])) { acc += (double)d / (double)(1ull << d); continue; }
+            st_node[sp] = tree[v].izero; st_depth[sp++] = d + 1;
+            st_node[sp] = tree[v].ione;  st_depth[sp++] = d + 1;
+        }
+        out->implied_avg_len = acc;
+        /* measured: fib4g (mean 3.0 bits) emits 7 % faster through an 11-bit table (half the
+         * shared memory: 4 CTAs per SM instead of 3), english1g (4.26) 11 % slower */
+        out->wf64 = acc <= 3.5 ? HB_WF_MAX - 1 : HB_WF_MAX;
+    }
     int frc = small ? HB_OK : build_fast_tables(tree, out);
     if (frc != HB_OK) { hb_lut_free(out); return frc; }
     frc = build_fsm(tree, nodes, out, !small);
@@ -283,7 +301,8 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
     out->wf = wf;
     out->stab = (uint32_t *)malloc(sizeof(uint32_t) * n);
     out->etab = (uint32_t *)malloc(sizeof(uint32_t) * n);
-    out->e64 = (uint32_t *)malloc(sizeof(uint32_t) * 2 * n);
+    const uint32_t wf64 = out->wf64;
+    out->e64 = (uint32_t *)malloc(sizeof(uint32_t) * 2 * ((size_t)1 << wf64));
     if (!out->stab || !out->etab || !out->e64) return HB_ERR_NOMEM;
     for (uint32_t x = 0; x < n; x++) {
         uint32_t sm = 0, nsym = 0, used = 0;       /* unlimited symbols (S-table) */
@@ -306,7 +325,7 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
                 e_nsym++;
                 e_used = p;
             }
-            if (x_nsym < HB_E64_MAXSYM) {
+            if (x_nsym < HB_E64_MAXSYM && p <= wf64) {
                 x_syms |= (uint32_t)tree[node].sym << (8 * x_nsym);
                 x_nsym++;
                 x_used = p;
@@ -317,13 +336,18 @@ static int build_fast_tables(const hb_node *tree, hb_lut *out) {
         if (nsym == 0) {
             out->stab[x] = HB_FAST_MARK << 16;
             out->etab[x] = HB_FAST_MARK << 16;
-            out->e64[2 * x] = 0;
-            out->e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
         } else {
-            out->e64[2 * x] = x_syms;
-            out->e64[2 * x + 1] = (0x3210u + 0x1111u * x_nsym) | ((8u * x_nsym) << 16) | (x_used << 26);
             out->stab[x] = sm | (used << 16) | (nsym << 24);
             out->etab[x] = e_syms | (e_used << 16) | (e_nsym << 24);
+        }
+        if (x < (1u << wf64)) {   /* only the low wf64 index bits count for this table */
+            if (x_nsym == 0) {
+                out->e64[2 * x] = 0;
+                out->e64[2 * x + 1] = 0x3210u | (HB_E64_MARK << 26);
+            } else {
+                out->e64[2 * x] = x_syms;
+                out->e64[2 * x + 1] = (0x3210u + 0x1111u * x_nsym) | ((8u * x_nsym) << 16) | (x_used << 26);
+            }
         }
     }
     return HB_OK;

@@ -38,11 +38,13 @@ typedef struct hb_lut {
     uint16_t *fsm_bstep;   /* fsm_states * 2 entries */
     uint8_t   fsm_depth[256];
     uint16_t  fsm_pstep[256];
-    uint32_t *e64;         /* E64-table: 2 << wf words (lo, hi interleaved) */
+    uint32_t *e64;         /* E64-table: 2 << wf64 words (lo, hi interleaved) */
     /* transducer state numbering (breadth first, root = 0): node index of every state
      * and state of every node (-1 for leaves); node_state has `nodes` entries */
     int32_t   fsm_node[256];
     int32_t  *node_state;
+    uint32_t  wf64;              /* index width of the E64-table (hb_format.h) */
+    double    implied_avg_len;   /* sum over leaves of 2^-len * len */
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the

@@ -407,7 +407,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, uint32_t wf64) {
     Emul<WPT, T> E;
     E.emit_mode = emit_mode;
     E.sync_mode = sync_mode;
@@ -418,7 +418,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
-    E.tbE64 = hb_tables64{e64, 0u, ((1u << wf) - 1u) << 3, slow};
+    E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow};
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
@@ -458,13 +458,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
                         const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
-                        const uint32_t *e64) {
+                        const uint32_t *e64, uint32_t wf64) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep, emit_mode, e64)
+                          fsm_depth, fsm_pstep, emit_mode, e64, wf64)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

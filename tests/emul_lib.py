@@ -43,7 +43,7 @@ def lib():
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                C.c_void_p, C.POINTER(Stats), C.c_uint32,
                                C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_int, C.c_void_p]
+                               C.c_int, C.c_void_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -82,7 +82,7 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
                         out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win,
                         sync_mode, lut["fsm_states"], fsm.ctypes.data, fdepth.ctypes.data,
-                        fpstep.ctypes.data, emit_mode, e64.ctypes.data)
+                        fpstep.ctypes.data, emit_mode, e64.ctypes.data, lut["wf64"])
     return out, smap, res, st.as_dict(), rc
 
 

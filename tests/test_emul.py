@@ -300,20 +300,40 @@ def test_emit_paths(name, mode, shape):
 def test_e64_table():
     """E64 entries against the E-/S-table semantics: up to four symbols, the window
     selector, 8 * nsym, bits consumed, marker where no codeword fits"""
-    st = _stream("world192")   # 20-bit codes: markers exist
-    lut = hb.build_lut(st.tree)
-    e64 = lut["e64"].reshape(-1, 2)
-    stab = lut["stab"]
     marks = 0
-    for x in range(1 << lut["wf"]):
+    for tree in (_stream("world192").tree,                       # 20-bit codes: markers exist, 12-bit index
+                 hb.Model(hb.MODEL_FIBONACCI).tree):             # short codes: 11-bit index
+        marks += _check_e64(tree)
+    assert marks > 0
+
+
+def _check_e64(tree):
+    class _S:   # the loop below only needs .tree
+        pass
+    st = _S()
+    st.tree = tree
+    lut = hb.build_lut(st.tree)
+    wf64 = lut["wf64"]
+    assert wf64 == (11 if lut["implied_avg_len"] <= 3.5 else 12)
+    e64 = lut["e64"].reshape(-1, 2)
+    assert e64.shape[0] == 1 << wf64
+    marks = 0
+    for x in range(1 << wf64):
         syms, meta = int(e64[x, 0]), int(e64[x, 1])
         ns, bits = (meta >> 19) & 7, meta >> 26
         assert (meta >> 16) & 0x3FF == 8 * ns and (meta & 0xFFFF) == 0x3210 + 0x1111 * ns
-        if (int(stab[x]) >> 24) == 0:
+        # greedy walk over the wf64 index bits: how many whole codewords fit (at most four)
+        node, pos, fit, last = 0, 0, 0, 0
+        while pos < wf64 and fit < 4:
+            node = int(st.tree[node]["ione"] if (x >> pos) & 1 else st.tree[node]["izero"])
+            pos += 1
+            if st.tree[node]["izero"] == -1:
+                fit, last, node = fit + 1, pos, 0
+        if fit == 0:
             assert ns == 0 and bits == 48 and syms == 0
             marks += 1
             continue
-        assert 1 <= ns <= 4 and ns == min(4, int(stab[x]) >> 24)
+        assert ns == fit and bits == last
         # walk the tree over the index bits
         node, pos, got = 0, 0, []
         while len(got) < ns:
@@ -323,7 +343,8 @@ def test_e64_table():
                 got.append(int(st.tree[node]["sym"]))
                 node = 0
         assert pos == bits and got == [(syms >> (8 * i)) & 0xFF for i in range(ns)]
-    assert marks > 0
+        assert syms >> (8 * ns) == 0 if ns < 4 else True
+    return marks
 
 
 @pytest.mark.parametrize("shape", [(8, 256), (2, 8)])
