@@ -802,8 +802,11 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
  * words assembled in a register window, each thread's last partial word stored
  * byte-wise after a barrier; software-pipelined tile loads; bulk-store wait deferred to
  * the next window.  Probes read the E64-table (up to four symbols per probe). */
+#ifndef HB_EMITW_MIN_CTAS
+#define HB_EMITW_MIN_CTAS 4
+#endif
 template <int WPT>
-__global__ void __launch_bounds__(HB_T, 4)
+__global__ void __launch_bounds__(HB_T, HB_EMITW_MIN_CTAS)
 hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
                uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
