@@ -6,9 +6,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, huffmandecoderongpus_b200 as hb, oracle_lib as O
 dev=torch.device("cuda:0")
-ctx=hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+wpt = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+ctx=hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
 if len(sys.argv) > 1: ctx.set_phase_timing(sys.argv[1])   # always | never | auto
-for name in ("hello","paper1","kjv","ecoli"):
+for name in ("hello","paper1","news","world192","kjv","ecoli"):
     f=hb.HuffFile.load(O.corpus_path(name))
     cb=hb.Codebook(ctx,f.tree)
     n=(f.nbytes+15)//16*16+16
