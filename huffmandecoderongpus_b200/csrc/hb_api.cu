@@ -60,6 +60,8 @@ struct hb_ctx {
     int host_nodes = 0;
     /* pipelined host path: copy streams, per-chunk events, pinned staging */
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_aux = nullptr;            /* the partial tile's sync kernel, beside the transducer kernel */
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaEvent_t *pipe_ev = nullptr;   /* 2 per chunk: upload done, emit done */
     int pipe_cap = 0;
     uint64_t *h_pipe = nullptr;       /* pinned: 32 map words + 4 entry/base words per chunk */
@@ -159,6 +161,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     free(ctx->pipe_ev);
     if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
     if (ctx->pipe_t0) { cudaEventDestroy(ctx->pipe_t0); cudaEventDestroy(ctx->pipe_t1); }
+    if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); cudaEventDestroy(ctx->aux_fork); cudaEventDestroy(ctx->aux_join); }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->d_eb.p) cudaFree(ctx->d_eb.p);
@@ -498,20 +501,34 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
         const uint32_t n_full = (uint32_t)(a.bits_own / ((uint64_t)HB_T * 32u * WPT));
         const uint32_t min_tiles = ctx->sync_path == HB_SYNC_FSM ? 1u
                                  : 2u * HB_SYNC_MIN_CTAS * (uint32_t)ctx->prop.multiProcessorCount;
-        if (n_full >= min_tiles) {
-            if ((rc = launch_fsm_sync<WPT>(ctx, cb, a, n_full))) return rc;
-            tile0 = n_full;
+        if (n_full >= min_tiles) tile0 = n_full;
+    }
+    const bool split = tile0 > 0 && tile0 < a.ntiles;   /* transducer kernel + one partial tile */
+    cudaStream_t probe_stream = ctx->stream;
+    if (split) {
+        /* the partial tile's single CTA goes FIRST, on a forked stream: it finds a free slot
+         * now, whereas behind the persistent transducer kernel it would run alone at the end */
+        if (!ctx->s_aux) {
+            CK(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
         }
+        CK(cudaEventRecord(ctx->aux_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_aux, ctx->aux_fork, 0));
+        probe_stream = ctx->s_aux;
     }
     if (tile0 < a.ntiles) {
         size_t smem = sync_smem_bytes<WPT>(a.wf);
         int grid = 1;
         if ((rc = grid_for(ctx, hb_sync_kernel<WPT>, smem, a.ntiles - tile0, &grid))) return rc;
-        hb_sync_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(a, tile0, (uint16_t *)ctx->subs.p,
+        hb_sync_kernel<WPT><<<grid, HB_T, smem, probe_stream>>>(a, tile0, (uint16_t *)ctx->subs.p,
                                                                (uint32_t *)ctx->tmaps.p);
         CK(cudaGetLastError());
         ctx->last_launches++;
     }
+    if (split) CK(cudaEventRecord(ctx->aux_join, ctx->s_aux));
+    if (tile0 > 0 && (rc = launch_fsm_sync<WPT>(ctx, cb, a, tile0))) return rc;
+    if (split) CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
     if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->map_fused = ctx->fuse_small && ncta == 1 && !d_map;
     if (!ctx->map_fused) {
