@@ -574,19 +574,19 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
             scan_launches = 2;
         }
     } else {
-        hb_scan_down_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
-            (const uint32_t *)ctx->tmaps.p, a.ntiles, (const uint64_t *)ctx->wmaps.p,
+        /* down-sweep; the owner of a tile whose true entry offset is not 0 re-chains its head */
+        hb_scan_downfix_kernel<WPT><<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
+            a, (const uint32_t *)ctx->tmaps.p, (const uint64_t *)ctx->wmaps.p,
             (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
-            (uint64_t *)ctx->tile_base.p, misc + 32, a.bits_own, a.bits_avail);
+            (uint64_t *)ctx->tile_base.p, misc + 32, (uint16_t *)ctx->subs.p);
         CK(cudaGetLastError());
-        /* re-chain the head of every tile whose true entry offset is not 0 (S-table) */
-        if (a.minlen == a.maxlen)
+        scan_launches = 1;
+        if (a.minlen == a.maxlen) {
             hb_fix_fixed_kernel<WPT><<<a.ntiles, HB_T, 0, ctx->stream>>>(
                 a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
-        else
-            hb_fix_kernel<WPT><<<(a.ntiles + HB_T - 1) / HB_T, HB_T, 0, ctx->stream>>>(
-                a, (const uint8_t *)ctx->tile_entry.p, (uint16_t *)ctx->subs.p);
-        CK(cudaGetLastError());
+            CK(cudaGetLastError());
+            scan_launches = 2;
+        }
     }
     ctx->last_launches += scan_launches + 1;   /* + the emit kernel below */
     if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[3], ctx->stream));

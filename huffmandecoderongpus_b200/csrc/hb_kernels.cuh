@@ -564,19 +564,39 @@ __global__ void hb_compose_kernel(const uint64_t *__restrict__ all_maps, int n_r
     entry_base[2] = base;
 }
 
-/* down-sweep: fix the entry offset and output base of every tile.
+/* One stream word of a tile for hb_fix_entries (0 past the end of the data). */
+struct hb_tile_words {
+    const uint32_t *words;
+    uint64_t base, nwords;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return base + i < nwords ? __ldg(words + base + i) : 0u;
+    }
+};
+
+/* down-sweep + fix: the entry offset and output base of every tile, and -- where a tile's
+ * true entry offset differs from the hypothesis the sync kernel recorded (0) -- the
+ * (entry, count) records of its leading subsequences (typically 1-2) re-chained in place
+ * by the thread that owns the tile (S-table; fixed-length codes: hb_fix_fixed_kernel).
  * result[0] = symbols of this shard, [1] = exit offset, [2] = entry, [3] = base.
- * One CTA more than needed is harmless; launched after hb_scan_top_kernel. */
+ * Launched after hb_scan_top_kernel. */
+template <int WPT>
 __global__ void __launch_bounds__(HB_SCAN_T)
-hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
-                    const uint64_t *__restrict__ wmaps, const uint64_t *__restrict__ cprefix,
-                    const uint64_t *__restrict__ shard_map,
-                    const uint64_t *__restrict__ entry_base,
-                    uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
-                    uint64_t *__restrict__ result, uint64_t bits_own, uint64_t bits_avail) {
+hb_scan_downfix_kernel(hb_stream_args a, const uint32_t *__restrict__ tmaps,
+                       const uint64_t *__restrict__ wmaps, const uint64_t *__restrict__ cprefix,
+                       const uint64_t *__restrict__ shard_map,
+                       const uint64_t *__restrict__ entry_base,
+                       uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
+                       uint64_t *__restrict__ result, uint16_t *__restrict__ subs) {
+    constexpr int T = HB_T;
+    constexpr uint32_t TS = T * 32u * WPT;
+    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* S-table, for the fix step */
     __shared__ uint32_t s_we[32];
     __shared__ uint64_t s_wb[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ntiles = a.ntiles;
+    const bool fixed_len = a.minlen == a.maxlen;
+    if (!fixed_len)
+        for (uint32_t i = threadIdx.x; i < (1u << a.wf); i += HB_SCAN_T) s_fast[i] = __ldg(a.fast + i);
     const uint32_t E = entry_base ? (uint32_t)entry_base[0] & 31u : 0u;
     const uint64_t B = entry_base ? entry_base[1] : 0ull;
     const uint64_t cp = __ldg(cprefix + (uint64_t)blockIdx.x * 32 + E);
@@ -585,7 +605,7 @@ hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
         uint64_t total = sm >> 8;
         /* the serial decoder emits a symbol only on reaching a leaf: a last
          * codeword that runs past the end of the data is not a symbol */
-        if (total && bits_own + (sm & 31u) > bits_avail) total--;
+        if (total && a.bits_own + (sm & 31u) > a.bits_avail) total--;
         result[0] = total;
         result[1] = sm & 31u;
         result[2] = E;
@@ -630,46 +650,19 @@ hb_scan_down_kernel(const uint32_t *__restrict__ tmaps, uint32_t ntiles,
         cur = m & 31u;
     }
     const uint64_t tile = gw * 32 + lane;
-    if (tile < ntiles) {
-        tile_entry[tile] = (uint8_t)my_e;
-        tile_base[tile] = my_b;
-    }
-}
-
-/* ------------------------------------------------------------------------- */
-/* One thread per tile: where the tile's true entry offset differs from the
- * hypothesis the sync kernel recorded (0), re-chain the leading subsequences
- * (typically 1-2) and rewrite their (entry, count) records in place.  All tiles
- * in parallel; uses the S-table, so the emit kernel needs only the E-table. */
-struct hb_tile_words {
-    const uint32_t *words;
-    uint64_t base, nwords;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-        return base + i < nwords ? __ldg(words + base + i) : 0u;
-    }
-};
-
-template <int WPT>
-__global__ void __launch_bounds__(HB_T)
-hb_fix_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry, uint16_t *__restrict__ subs) {
-    constexpr int T = HB_T;
-    constexpr uint32_t TS = T * 32u * WPT;
-    __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];
-    for (uint32_t i = threadIdx.x; i < (1u << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
-    __syncthreads();
+    if (tile >= ntiles) return;
+    tile_entry[tile] = (uint8_t)my_e;
+    tile_base[tile] = my_b;
+    if (my_e == 0 || fixed_len) return;
     hb_tables tb;
     tb.fast = s_fast;
-    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
+    tb.fast_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
     tb.fmask4 = ((1u << a.wf) - 1u) << 2;
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
-    const uint32_t tile = blockIdx.x * T + threadIdx.x;
-    if (tile >= a.ntiles) return;
-    const uint32_t E = tile_entry[tile];
-    if (E == 0) return;
-    const uint64_t own_left = a.bits_own - (uint64_t)tile * TS;
+    const uint64_t own_left = a.bits_own - tile * TS;
     const uint32_t tile_lim = own_left < TS ? (uint32_t)own_left : TS;
-    hb_tile_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
-    hb_fix_entries<WPT, T>(tb, word, subs + (uint64_t)tile * T, tile_lim, E);
+    hb_tile_words word{a.words, tile * (T * WPT), a.nwords};
+    hb_fix_entries<WPT, T>(tb, word, subs + tile * T, tile_lim, my_e);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -844,7 +837,7 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     uint64_t B = 0;
     if (tile < a.ntiles) {
         hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-        sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
+        sub = subs[(uint64_t)tile * T + t];   /* already re-chained by the down-sweep kernel */
         B = tile_base[tile];
     }
     while (tile < a.ntiles) {
@@ -979,7 +972,7 @@ hb_emit_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
         const uint64_t B = tile_base[tile];
         uint32_t w[WPT + 1];
         hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-        const uint16_t sub = subs[(uint64_t)tile * T + t];   /* already re-chained by hb_fix_kernel */
+        const uint16_t sub = subs[(uint64_t)tile * T + t];   /* already re-chained by the down-sweep kernel */
 
         const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
         uint32_t nk;
