@@ -806,7 +806,7 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
-    constexpr uint32_t EW = 2u;                                  /* words per table entry */
+    constexpr uint32_t EW = 2u;                            /* words per E64 entry */
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_fast = smem;                               /* E64-table: 2 << a.wf words (a.wf = its own width) */
     uint32_t *s_warp = smem + (EW << a.wf);                /* 16 */
@@ -815,16 +815,11 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
 
     for (uint32_t i = t; i < (EW << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
     __syncthreads();
-    hb_tables tb;
-    tb.fast = s_fast;
-    tb.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
-    tb.fmask4 = ((1u << a.wf) - 1u) << 2;
-    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
     hb_tables64 tb64;
     tb64.fast = s_fast;
-    tb64.fast_saddr = tb.fast_saddr;
+    tb64.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
     tb64.fmask = ((1u << a.wf) - 1u) << 3;
-    tb64.slow = tb.slow;
+    tb64.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
 
@@ -841,11 +836,6 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
         B = tile_base[tile];
     }
     while (tile < a.ntiles) {
-        if (false) {
-            hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
-            sub = subs[(uint64_t)tile * T + t];
-            B = tile_base[tile];
-        }
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
         const uint32_t next = tile + gridDim.x;
