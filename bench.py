@@ -200,7 +200,9 @@ def main():
     ap.add_argument("--workload", default="english1g", choices=list(WORKLOADS))
     ap.add_argument("--wpt", type=int, default=0, help="words per thread (0 = library default)")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words"],
+    ap.add_argument("--ep-wf", type=int, default=0, help="EP-table index bits of the flat emit kernel (0 = auto)")
+    ap.add_argument("--ep-copies-log2", type=int, default=-1, help="log2 of the EP-table copies (-1 = auto)")
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat"],
                     help="staging stores: bytes (hb_emit_kernel) or whole words (hb_emitw_kernel, default)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe", "fsm"],
                     help="auto: transducer sync kernel on full tiles; probe: probe sync kernel only")
@@ -243,6 +245,7 @@ def main():
     if args.host_chunk_mib:
         ctx.set_host_chunk(args.host_chunk_mib << 20)
     ctx.set_emit_path(args.emit_path)
+    ctx.set_emit_table(args.ep_wf, args.ep_copies_log2)
     model = hb.Model(kind)
     cb = hb.Codebook(ctx, model.tree)
 
@@ -331,7 +334,7 @@ def main():
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
     sync_name = "hb_sync_kernel" if args.sync_path == "probe" else "hb_fsm_sync_kernel"
-    emit_name = "hb_emit_kernel" if args.emit_path == "bytes" else "hb_emitw_kernel"
+    emit_name = {"bytes": "hb_emit_kernel", "words": "hb_emitw_kernel"}.get(args.emit_path, "hb_emitf_kernel")
     dom_name = {"sync": sync_name, "emit": emit_name}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this

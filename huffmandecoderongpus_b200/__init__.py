@@ -109,6 +109,7 @@ def lib():
     L.hb_ctx_set_phase_timing.argtypes = [vp, i32]
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
+    L.hb_ctx_set_emit_table.argtypes = [vp, i32, i32]
     L.hb_ctx_sync.argtypes = [vp]
     L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
     L.hb_ctx_timing_begin.argtypes = [vp, i32]
@@ -280,9 +281,15 @@ class Context:
                "hb_ctx_set_phase_timing")
 
     def set_emit_path(self, path):
-        """staging stores: "bytes", "words" (whole 32-bit words) or "auto" (= words)."""
-        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2}[path]),
+        """emit kernel: "bytes" (byte stores), "words" (whole 32-bit words, one loop per stream
+        word), "flat" (hb_emitf_kernel on every tile but the last; experimental, slower) or
+        "auto" (= words)."""
+        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2, "flat": 3}[path]),
                "hb_ctx_set_emit_path")
+
+    def set_emit_table(self, index_bits=0, log2_copies=-1):
+        """EP-table geometry of the flat emit kernel (0 / -1 = automatic)."""
+        _check(lib().hb_ctx_set_emit_table(self.h, index_bits, log2_copies), "hb_ctx_set_emit_table")
 
     def set_sync_path(self, path):
         """"auto" (transducer sync kernel for streams of two waves of tiles or more), "probe"

@@ -36,6 +36,7 @@ struct hb_ctx {
     int ctas_per_sm = 0;
     int sync_path = HB_SYNC_AUTO;
     int emit_path = HB_EMIT_AUTO;
+    int ep_wf = 0, ep_rshift = -1;   /* EP-table geometry of the flat emit kernel (0 / -1 = automatic) */
     int phase_timing = HB_PHASES_AUTO;
     bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
     bool map_fused = false;       /* the last hb_shard_map left up/top to hb_scan_small_kernel */
@@ -197,8 +198,18 @@ extern "C" int hb_ctx_set_phase_timing(hb_ctx *ctx, int mode) {
 }
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
-    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS)) return HB_ERR_ARG;
+    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS && path != HB_EMIT_FLAT))
+        return HB_ERR_ARG;
     ctx->emit_path = path;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_set_emit_table(hb_ctx *ctx, int index_bits, int log2_copies) {
+    if (!ctx) return HB_ERR_ARG;
+    if (index_bits != 0 && (index_bits < HB_EP_WF_MIN || index_bits > HB_EP_WF_MAX)) return HB_ERR_ARG;
+    if (log2_copies < -1 || log2_copies > 4) return HB_ERR_ARG;
+    ctx->ep_wf = index_bits;
+    ctx->ep_rshift = log2_copies;
     return HB_OK;
 }
 
@@ -552,6 +563,65 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
     return HB_OK;
 }
 
+/* Flat emit kernel over tiles [0, ntiles_run): EP-table geometry, group count, window. */
+template <int G, int NP>
+static int run_emit_flat(hb_ctx *ctx, const hb_stream_args &ae, uint32_t rshift, uint32_t ntiles_run,
+                         void *d_out, uint64_t out_capacity, uint32_t win, uint32_t stage, size_t smem) {
+    CK(cudaFuncSetAttribute(hb_emitf_kernel<8, G, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t grid = (uint64_t)ctx->prop.multiProcessorCount;
+    const uint64_t need = ((uint64_t)ntiles_run + G - 1) / G;
+    if (grid > need) grid = need;
+    uint64_t *misc = misc_words(ctx);
+    hb_emitf_kernel<8, G, NP><<<(int)grid, G * HB_T, smem, ctx->stream>>>(
+        ae, rshift, ntiles_run, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+        (uint8_t *)d_out, out_capacity, win, stage, (uint32_t *)(misc + 36));
+    CK(cudaGetLastError());
+    return HB_OK;
+}
+
+static int launch_emit_flat(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a, uint32_t ntiles_run,
+                            void *d_out, uint64_t out_capacity, bool *launched) {
+    *launched = false;
+    hb_stream_args ae = a;
+    uint32_t wf = ctx->ep_wf ? (uint32_t)ctx->ep_wf : 10u;
+    if (wf > cb->lut.maxlen && cb->lut.maxlen >= HB_EP_WF_MIN) wf = cb->lut.maxlen;   /* no longer codeword exists */
+    uint32_t rshift = ctx->ep_rshift >= 0 ? (uint32_t)ctx->ep_rshift : 4u;
+    const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
+    while (rshift > 0 && ((size_t)8 << (wf + rshift)) > limit / 2 + limit / 8) rshift--;
+    ae.wf = wf;
+    const size_t table = (size_t)8 << (wf + rshift);
+    /* staging window: the expected output of a tile plus head room, shrunk (never below one
+     * thread's worth) until at least two groups fit beside the table */
+    uint32_t win = 0, stage = 0;
+    stage_geometry(cb, 8, &win, &stage);
+    const uint32_t max_c = (256u + cb->lut.minlen - 1) / cb->lut.minlen;
+    int G = 0;
+    for (int g = 4; g >= 2 && !G; g--) {
+        const size_t per = (limit - table) / (size_t)g;
+        const size_t fixed = sizeof(uint32_t) * (size_t)hb_emitf_group_words<8>(0);
+        if (per < fixed + max_c + 64u) continue;
+        uint32_t w = (uint32_t)((per - fixed - max_c - 32u) & ~(size_t)15);
+        if (g > 2 && w < win - win / 8) continue;     /* rather fewer groups than many windows per tile */
+        if (w < ((max_c + 15u) & ~15u)) continue;
+        if (w < win) { win = w; stage = (w + max_c + 16u + 15u) & ~15u; }
+        G = g;
+    }
+    if (!G) return HB_OK;
+    const size_t smem = table + (size_t)G * sizeof(uint32_t) * hb_emitf_group_words<8>(stage);
+    const bool np3 = wf <= 10u;
+    int rc = HB_OK;
+    switch (G * 2 + (np3 ? 1 : 0)) {
+    case 9: rc = run_emit_flat<4, 3>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    case 8: rc = run_emit_flat<4, 2>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    case 7: rc = run_emit_flat<3, 3>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    case 6: rc = run_emit_flat<3, 2>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    case 5: rc = run_emit_flat<2, 3>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    case 4: rc = run_emit_flat<2, 2>(ctx, ae, rshift, ntiles_run, d_out, out_capacity, win, stage, smem); break;
+    }
+    if (rc == HB_OK) *launched = true;
+    return rc;
+}
+
 template <int WPT>
 static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a,
                        const uint64_t *d_entry_base, void *d_out, uint64_t out_capacity) {
@@ -595,15 +665,24 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     stage_geometry(cb, WPT, &win, &stage);
     size_t smem = emit_smem_bytes(a.wf, stage);
     int grid = 1;
+    /* on request (A/B, tests): all tiles but the last one through the flat kernel.  Measured
+     * slower than hb_emitw_kernel on both bench workloads (profiles/r02a_flat_emit.md), so
+     * HB_EMIT_AUTO never picks it. */
+    uint32_t tile0 = 0;
+    if (WPT == 8 && ctx->emit_path == HB_EMIT_FLAT && a.ntiles >= 2) {
+        bool launched = false;
+        if ((rc = launch_emit_flat(ctx, cb, a, a.ntiles - 1u, d_out, out_capacity, &launched))) return rc;
+        if (launched) { tile0 = a.ntiles - 1u; ctx->last_launches++; }
+    }
     /* staging stores: whole words, three symbols per probe (english1g 0.75 ms vs 0.81 with
      * byte stores); the byte-store kernel on request */
     if (ctx->emit_path != HB_EMIT_BYTES) {
         ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
         ae.wf = cb->lut.wf64;                     /* ... and its own index width */
         smem += (size_t)8 << ae.wf;               /* the table sits in front of the staging buffer */
-        if ((rc = grid_for(ctx, hb_emitw_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
+        if ((rc = grid_for(ctx, hb_emitw_kernel<WPT>, smem, a.ntiles - tile0, &grid))) return rc;
         hb_emitw_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
-            ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+            ae, tile0, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
             (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
             (uint32_t *)(misc + 36));
     } else {

@@ -575,6 +575,194 @@ HB_HD void hb_store_tail(const hb_tail &tl) {
         if (i < tl.k) hb_st8(tl.at, i, tl.bytes >> (8u * i));
 }
 
+/* ==== flat emit walk (hb_emitf_kernel) =========================================
+ * One loop over the whole chain of a subsequence instead of one loop per stream word: the
+ * words come from shared memory (a column per thread, so the reads are conflict free) into
+ * a 64-bit shifting buffer, the probes read the EP-table (hb_format.h) whose copies keep the
+ * lanes of a warp on disjoint banks.
+ *   buffer: (hi:lo) holds the next stream bits from bit 0 up and ONE marker bit directly
+ *           above them, so "fewer than 32 valid bits" is `hi == 0` and no counter is kept;
+ *           a refill ORs the next word in at the marker and moves the marker up 32.
+ *   body:   at most one refill, then NP probes of at most wfp bits (NP * wfp <= 32 + the
+ *           wfp bits the last probe of a body must still find: NP = 3 for wfp <= 10, else 2).
+ *   long codewords (marker entry): consume nothing, so the rest of the body repeats the
+ *           same probe; the next body decodes that one codeword with the single-symbol table.
+ *   ownership of staging words: a thread stores WHOLE words only -- every word that holds
+ *           one of its bytes -- and stops when the word holding its last byte is complete.
+ *           The symbols that complete that word are the first ones of the right neighbour's
+ *           chain, which this chain simply runs on into.  The first word of a slice may
+ *           begin before the slice (those lanes hold zeros); it is the left neighbour's
+ *           final word, which every thread therefore returns and stores once more after
+ *           the barrier that ends the decode phase.  No symbol is ever clipped. */
+struct hb_ptab {
+    const uint32_t *tab;   /* plain EP-table, two words per entry (host emulation) */
+    uint32_t saddr;        /* device: shared address of the replicated table + this lane's copy */
+    uint32_t shift;        /* 3 + rshift */
+    uint32_t mask;         /* ((1 << wfp) - 1) << shift */
+    hb_lutref slow;
+};
+
+/* EP-table entry of index x (wfp bits, LSB first) from the single-symbol table */
+HB_HD void hb_ep_entry(const hb_lutref &slow, uint32_t x, uint32_t wfp, uint32_t *lo, uint32_t *hi) {
+    uint32_t pos = 0, n = 0, syms = 0;
+    while (n < HB_E64_MAXSYM && pos < wfp) {
+        uint32_t sym;
+        const uint32_t len = hb_probe(slow, x >> pos, 0u, 0u, &sym);
+        if (pos + len > wfp) break;          /* would use bits beyond the index */
+        syms |= sym << (8u * n);
+        n++;
+        pos += len;
+    }
+    *lo = syms;
+    *hi = n ? ((0x3210u + 0x1111u * n) | (pos << 16) | ((8u * n) << 21)) : (0x3210u | HB_EP_MARK);
+}
+
+HB_HD uint32_t hb_flo(uint32_t v) {   /* index of the highest set bit, v != 0 */
+#ifdef __CUDA_ARCH__
+    return 31u - (uint32_t)__clz((int)v);
+#else
+    return 31u - (uint32_t)__builtin_clz(v);
+#endif
+}
+
+/* Col: next() returns the next stream word of the thread's chain (its own words, then the
+ * following subsequences'); e: entry offset; out/mis: first staging byte and its address & 3;
+ * wend: end of the last staging word to store.  Returns that last word.
+ * This C version is what the CPU emulation runs; the kernel runs hb_emit_flat_dev below, the
+ * same loop with its predication written out in PTX. */
+template <int NP, class Col>
+HB_HD uint32_t hb_emit_flat(const hb_ptab &tb, Col &col, uint32_t e, hb_out_t out, uint32_t mis,
+                            hb_out_t wend) {
+    const uint32_t w0 = col.next();
+    uint32_t lo = hb_funnel_r(w0, 1u, e), hi = e ? 0u : 1u;   /* ((1 << 32) | w0) >> e */
+    uint32_t pend = 0u, posk = 8u * mis, word = 0u, m = 0u;
+    hb_out_t wpp = out - mis;
+    for (;;) {
+        if (hi == 0u) {                       /* marker inside lo: fewer than 32 valid bits */
+            const uint32_t w = col.next();
+            const uint32_t v = hb_flo(lo), mk = 1u << v;
+            lo = (lo ^ mk) | (w << v);
+            hi = hb_funnel_l(w, 0u, v) | mk;  /* w >> (32 - v), 0 for v == 0 */
+        }
+        if (m & HB_EP_MARK) {                 /* one codeword longer than the table index */
+            uint32_t sym;
+            const uint32_t len = hb_probe(tb.slow, lo, hi, 0u, &sym);   /* >= 32 valid bits here */
+            word = hb_funnel_l(pend, sym, posk);
+            pend = hb_prmt(pend, sym, 0x4321u);
+            const uint32_t posk_n = posk + 8u;
+            if (len >= 32u) { lo = hi; hi = 0u; }
+            else { lo = hb_funnel_r(lo, hi, len); hi >>= len; }
+            m = 0u;
+            if ((posk ^ posk_n) & 0x20u) {
+                hb_st32(wpp, 0u, word);
+                wpp += 4;
+                if (wpp == wend) return word;
+            }
+            posk = posk_n;
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            const uint32_t x = (lo << tb.shift) & tb.mask;
+            const uint32_t s = tb.tab[2u * (x >> tb.shift)];
+            m = tb.tab[2u * (x >> tb.shift) + 1u];
+            const uint32_t m2 = m >> 16;      /* [4:0] bits consumed */
+            word = hb_funnel_l(pend, s, posk);
+            const uint32_t posk_n = posk + (m >> 21);   /* + 8 * nsym (junk above bit 9) */
+            pend = hb_prmt(pend, s, m);
+            lo = hb_funnel_r(lo, hi, m2);
+            hi = hb_funnel_r(hi, 0u, m2);
+            if ((posk ^ posk_n) & 0x20u) {
+                hb_st32(wpp, 0u, word);
+                wpp += 4;
+                if (wpp == wend) return word;
+            }
+            posk = posk_n;
+        }
+    }
+}
+
+#ifdef __CUDACC__
+/* Device version.  cptr/stride: shared address of the thread's column and the byte distance
+ * between rows; laneoff: byte offset of this lane's table copy; tb.saddr: the table.
+ * Every probe is one straight-line block with two predicated instructions (the staging
+ * store and its pointer bump); the refill is one straight-line block predicated on
+ * `hi == 0`.  Written in PTX because the compiler turns the C loop above into branches
+ * around the store and the refill, which costs more warp instructions than it saves. */
+template <int NP>
+__device__ __forceinline__ uint32_t hb_emit_flat_dev(const hb_ptab &tb, uint32_t laneoff, uint32_t cptr,
+                                                     uint32_t stride, uint32_t e, uint32_t out,
+                                                     uint32_t mis, uint32_t wend) {
+    uint32_t w0;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(cptr));
+    cptr += stride;
+    uint32_t lo = __funnelshift_r(w0, 1u, e), hi = e ? 0u : 1u;
+    uint32_t pend = 0u, posk = 8u * mis, word = 0u, m = 0u;
+    uint32_t wpp = out - mis;
+    for (;;) {
+        asm volatile("{\n\t"
+                     ".reg .pred q;\n\t"
+                     ".reg .b32 w, v, mk, t;\n\t"
+                     "setp.eq.u32 q, %1, 0;\n\t"
+                     "@q ld.shared.u32 w, [%2];\n\t"
+                     "@q add.u32 %2, %2, %3;\n\t"
+                     "@q bfind.u32 v, %0;\n\t"
+                     "@q shl.b32 mk, 1, v;\n\t"
+                     "@q shl.b32 t, w, v;\n\t"
+                     "@q lop3.b32 %0, %0, mk, t, 0xBE;\n\t"      /* (lo ^ mk) | t */
+                     "@q shf.l.wrap.b32 t, w, 0, v;\n\t"         /* w >> (32 - v), 0 for v == 0 */
+                     "@q or.b32 %1, t, mk;\n\t"
+                     "}"
+                     : "+r"(lo), "+r"(hi), "+r"(cptr) : "r"(stride) : "memory");
+        if (m & HB_EP_MARK) {                 /* one codeword longer than the table index */
+            uint32_t sym;
+            const uint32_t len = hb_probe(tb.slow, lo, hi, 0u, &sym);
+            word = __funnelshift_l(pend, sym, posk);
+            pend = hb_prmt(pend, sym, 0x4321u);
+            const uint32_t posk_n = posk + 8u;
+            if (len >= 32u) { lo = hi; hi = 0u; }
+            else { lo = __funnelshift_r(lo, hi, len); hi >>= len; }
+            m = 0u;
+            if ((posk ^ posk_n) & 0x20u) {
+                asm volatile("st.shared.u32 [%0], %1;" :: "r"(wpp), "r"(word) : "memory");
+                wpp += 4;
+                if (wpp == wend) return word;
+            }
+            posk = posk_n;
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            asm volatile("{\n\t"
+                         ".reg .pred p;\n\t"
+                         ".reg .b32 t, x, s, m2, pk;\n\t"
+                         "shl.b32 t, %0, %8;\n\t"
+                         "lop3.b32 x, t, %9, %10, 0xEA;\n\t"     /* (t & mask) | laneoff */
+                         "add.u32 x, x, %11;\n\t"
+                         "ld.shared.v2.u32 {s, %6}, [x];\n\t"
+                         "shr.u32 m2, %6, 16;\n\t"
+                         "shf.l.wrap.b32 %5, %2, s, %3;\n\t"     /* staging word: pending bytes below the new ones */
+                         "shr.u32 pk, %6, 21;\n\t"
+                         "add.u32 pk, pk, %3;\n\t"
+                         "prmt.b32 %2, %2, s, %6;\n\t"
+                         "shf.r.wrap.b32 %0, %0, %1, m2;\n\t"
+                         "shf.r.wrap.b32 %1, %1, 0, m2;\n\t"
+                         "xor.b32 t, %3, pk;\n\t"
+                         "and.b32 t, t, 32;\n\t"
+                         "setp.ne.u32 p, t, 0;\n\t"
+                         "@p st.shared.u32 [%4], %5;\n\t"
+                         "@p add.u32 %4, %4, 4;\n\t"
+                         "mov.b32 %3, pk;\n\t"
+                         "}"
+                         : "+r"(lo), "+r"(hi), "+r"(pend), "+r"(posk), "+r"(wpp), "+r"(word), "+r"(m)
+                         : "r"(0), "r"(tb.shift), "r"(tb.mask), "r"(laneoff), "r"(tb.saddr)
+                         : "memory");
+            if (wpp == wend) return word;
+        }
+    }
+}
+#endif
+
 /* ==== tile-level walks over shared-memory copies ===========================
  * comp: the tile's T*WPT words followed by the first word of the next tile.
  * recs: converged records of the "tile entry offset 0" chain, recs[j*T + t].

@@ -32,6 +32,19 @@
 #define HB_E64_MARK 48u            /* > 31 + HB_WF_MAX: a position no real probe can reach */
 #define HB_WF_MAX 12               /* widest fast-table index (16 KB per table) */
 
+/* EP-table (flat emit kernel, hb_emitf_kernel): indexed by the next wfp stream bits; built by
+ * every CTA straight into shared memory from the single-symbol table, R = 1 << rshift copies
+ * interleaved entry by entry (copy r of entry x at byte (x << (3 + rshift)) + 8 r), so that
+ * the lanes of a warp read from disjoint banks (R = 16: lane l uses copy l & 15 and an LDS.64
+ * of a warp completes in its minimum of two wavefronts whatever the indices are).
+ *     lo: first .. fourth symbol, one byte each (at most HB_E64_MAXSYM)
+ *     hi: [15:0]  PRMT selector 0x3210 + 0x1111 * nsym
+ *         [20:16] bits consumed (<= wfp), [26:21] 8 * nsym
+ *         bit 31  marker: not even the first codeword fits wfp bits (nsym = 0, bits = 0) */
+#define HB_EP_MARK 0x80000000u
+#define HB_EP_WF_MIN 8
+#define HB_EP_WF_MAX 12
+
 /* Byte-step transducer of the sync kernel's fast path (the GPU counterpart of the
  * reference's jump table, framework/jumptableapproach.c:40-99, with jumpbits = 8 and
  * no symbol output).  States are the internal nodes of the tree, root = state 0, at

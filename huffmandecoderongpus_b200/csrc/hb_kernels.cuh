@@ -800,7 +800,7 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 #endif
 template <int WPT>
 __global__ void __launch_bounds__(HB_T, HB_EMITW_MIN_CTAS)
-hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
+hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
                uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
@@ -826,7 +826,7 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
     /* software pipeline: the next tile's words, record and output base are fetched as
      * soon as this tile's words are dead (after its last decode window), so that the
      * loads fly during the copy-out, the barriers and the next scan */
-    uint32_t tile = blockIdx.x, nwin = 0;
+    uint32_t tile = tile0 + blockIdx.x, nwin = 0;
     uint32_t w[WPT + 1];
     uint16_t sub = 0;
     uint64_t B = 0;
@@ -925,6 +925,183 @@ hb_emitw_kernel(hb_stream_args a, const uint16_t *__restrict__ subs,
             sub = subs[(uint64_t)next * T + t];
             B = tile_base[next];
         }
+        tile = next;
+    }
+    /* the staging buffer must outlive the last bulk store's reads */
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------------- */
+/* Emit kernel, flat variant (hb_emit_flat in hb_core.cuh): full tiles that are not the last
+ * tile of the shard.  A CTA is G groups of HB_T threads, each on its own tile behind its own
+ * named barrier, sharing ONE EP-table built in shared memory by the CTA itself (R copies,
+ * hb_format.h).  Per tile: the words go to shared memory transposed (word j of thread t at
+ * [j][t]: a thread's reads stay in its own bank whatever j is), rows WPT.. hold the first
+ * words of the next subsequence (the chain runs on into it until its last staging word is
+ * complete); group scan of the counts; the decode; barrier; every thread stores its final
+ * word once more (its right neighbour's first store has zeros in the shared lanes); the
+ * 16-byte-aligned middle of the window leaves as one TMA bulk copy. */
+#define HB_EMITF_LA 6       /* look-ahead rows: the chain may run (4 * 32 + 31 + 24) bits past the subsequence */
+template <int WPT>
+__host__ __device__ constexpr uint32_t hb_emitf_group_words(uint32_t stage_bytes) {
+    return 16u + (uint32_t)(WPT + HB_EMITF_LA) * HB_T + stage_bytes / 4u;
+}
+
+struct hb_col_smem {        /* a thread's column of the transposed tile */
+    uint32_t p, stride;
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p));
+        p += stride;
+        return v;
+    }
+};
+
+template <int WPT>
+__device__ __forceinline__ void hb_load_words_n(const hb_stream_args &a, uint64_t wbase, uint32_t (&w)[WPT]) {
+    if (wbase + WPT <= a.nwords) {
+        if (WPT % 8 == 0 && (reinterpret_cast<uintptr_t>(a.words) & 31u) == 0) {
+#pragma unroll
+            for (int v = 0; v < WPT / 8; v++)
+                asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[8 * v]), "=r"(w[8 * v + 1]), "=r"(w[8 * v + 2]), "=r"(w[8 * v + 3]),
+                               "=r"(w[8 * v + 4]), "=r"(w[8 * v + 5]), "=r"(w[8 * v + 6]), "=r"(w[8 * v + 7])
+                             : "l"(a.words + wbase + 8 * v));
+        } else {
+            const uint4 *p = reinterpret_cast<const uint4 *>(a.words + wbase);
+#pragma unroll
+            for (int v = 0; v < WPT / 4; v++) {
+                uint4 q = __ldg(p + v);
+                w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < WPT; j++)
+            w[j] = (wbase + j < a.nwords) ? __ldg(a.words + wbase + j) : 0u;
+    }
+}
+
+template <int WPT, int G, int NP>
+__global__ void __launch_bounds__(G * HB_T, 1)
+hb_emitf_kernel(hb_stream_args a, uint32_t rshift, uint32_t ntiles_run,
+                const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
+                uint8_t *__restrict__ out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
+                uint32_t *__restrict__ status) {
+    constexpr int T = HB_T;
+    constexpr uint32_t LA = HB_EMITF_LA;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t tab_words = 2u << (a.wf + rshift);
+    const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
+    uint32_t *s_grp = smem + tab_words + g * hb_emitf_group_words<WPT>(stage_bytes);
+    uint32_t *s_warp = s_grp;                              /* 16 */
+    uint32_t *s_w = s_grp + 16;                            /* (WPT + LA) rows of T words */
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_w + (WPT + LA) * T);   /* staging, 16-aligned */
+
+    const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
+    {   /* EP-table: every entry from the single-symbol table, R copies side by side */
+        const uint32_t R = 1u << rshift;
+        uint2 *tab = reinterpret_cast<uint2 *>(smem);
+        for (uint32_t x = threadIdx.x; x < (1u << a.wf); x += G * T) {
+            uint32_t lo, hi;
+            hb_ep_entry(slow, x, a.wf, &lo, &hi);
+            for (uint32_t r = 0; r < R; r++) tab[(x << rshift) + r] = make_uint2(lo, hi);
+        }
+    }
+    __syncthreads();
+    hb_ptab tb;
+    tb.tab = nullptr;
+    tb.shift = 3u + rshift;
+    tb.mask = ((1u << a.wf) - 1u) << tb.shift;
+    tb.saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(smem));
+    tb.slow = slow;
+    const uint32_t laneoff = (t & ((1u << rshift) - 1u)) << 3;   /* this lane's copy of the table */
+    const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
+    const uint32_t s_col_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_w) + 4u * t);
+
+    /* software pipeline: the next tile's words, record and output base are fetched as soon as
+     * this tile's decode has been issued */
+    const uint32_t tstep = gridDim.x * G;
+    uint32_t tile = blockIdx.x * G + g, nwin = 0;
+    uint32_t w[WPT], wl = 0u;
+    uint16_t sub = 0;
+    uint64_t B = 0;
+    auto fetch = [&](uint32_t tl) {
+        const uint64_t tb0 = (uint64_t)tl * (T * WPT);
+        hb_load_words_n<WPT>(a, tb0 + (uint64_t)t * WPT, w);
+        if (t < LA) wl = tb0 + T * WPT + t < a.nwords ? __ldg(a.words + tb0 + T * WPT + t) : 0u;
+        sub = subs[(uint64_t)tl * T + t];
+        B = tile_base[tl];
+    };
+    if (tile < ntiles_run) fetch(tile);
+    while (tile < ntiles_run) {
+        const uint32_t next = tile + tstep;
+        const uint64_t Bt = B;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) s_w[j * T + t] = w[j];
+        if (t > 0) {
+#pragma unroll
+            for (int j = 0; j < (int)LA; j++) s_w[(WPT + j) * T + t - 1] = w[j];
+        }
+        if (t < LA) s_w[(WPT + t) * T + T - 1] = wl;
+        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        uint32_t nk;
+        const uint32_t o = hb_group_exscan(c, s_warp, bar, t, &nk);
+        const bool full_out = Bt + nk > out_capacity;
+        if (full_out && t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
+
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; !full_out && (wb == 0 || wb < nk); wb += win, nwin++) {
+            const bool mine = c && o >= wb && o - wb < win;
+            const bool last_win = wb + win >= nk;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + Bt + wb) & 15u);
+            uint32_t *s_hi = s_warp + 14 + (nwin & 1u);     /* alternating slot: no barrier after the copy-out */
+            if (t == 0) {
+                /* the previous window's bulk store must have read the staging buffer */
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                *s_hi = nk;                                  /* default: last window */
+            }
+            hb_group_sync(bar);
+            uint32_t fin = 0u, fin_at = 0u;
+            if (mine) {
+                const uint32_t dst = s_out_saddr + al + (o - wb);
+                const uint32_t wend = (dst + c + 3u) & ~3u;
+                fin = hb_emit_flat_dev<NP>(tb, laneoff, s_col_saddr, 4u * T, e, dst, dst & 3u, wend);
+                fin_at = wend - 4u;
+                if (o + c - wb >= win && o + c < nk) *s_hi = o + c;   /* I am the window's last thread */
+            }
+            if (last_win && next < ntiles_run) fetch(next);
+            hb_group_sync(bar);
+            /* every in-loop store is done: the final word of each slice once more (its upper
+             * lanes are the right neighbour's first bytes, whose own first store zeroed the rest) */
+            if (mine) hb_st32((hb_out_t)fin_at, 0u, fin);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            hb_group_sync(bar);
+            const uint32_t hi_b = *s_hi;
+            if (lo_b < hi_b) {
+                uint8_t *gbase = out + Bt + wb - al;          /* 16-byte aligned */
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
+                if (a0 < a1) {
+                    if (t == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(gbase + a0), "r"(s_out_saddr + a0), "r"(a1 - a0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (t >= 32 && t < 64) {                 /* head and tail bytes, one warp */
+                        const uint32_t i = t - 32;
+                        if (begb + i < a0) gbase[begb + i] = s_out[begb + i];
+                        if (a1 + i < endb) gbase[a1 + i] = s_out[a1 + i];
+                    }
+                } else {
+                    for (uint32_t i = begb + t; i < endb; i += T) gbase[i] = s_out[i];   /* < 32 bytes */
+                }
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+        }
+        if (full_out && next < ntiles_run) fetch(next);
+        hb_group_sync(bar);       /* the tile's words are dead: the next iteration overwrites them */
         tile = next;
     }
     /* the staging buffer must outlive the last bulk store's reads */

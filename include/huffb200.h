@@ -101,7 +101,13 @@ int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 #define HB_EMIT_AUTO  0
 #define HB_EMIT_BYTES 1
 #define HB_EMIT_WORDS 2
+#define HB_EMIT_FLAT  3   /* hb_emitf_kernel (one loop per subsequence, lane-private table copies) on
+                             every tile but the last; 8 words per thread only.  Experimental: measured
+                             slower than HB_EMIT_WORDS, never chosen by HB_EMIT_AUTO */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
+/* EP-table of the flat emit kernel: index width in bits (8..12, 0 = automatic) and log2 of the
+ * number of copies interleaved in shared memory (0..4, -1 = automatic).  A/B knob. */
+int  hb_ctx_set_emit_table(hb_ctx *ctx, int index_bits, int log2_copies);
 /* hb_result's per-phase times need three extra CUDA events per decode (~4 us each).
  * HB_PHASES_AUTO records them for streams of more than 1024 tiles and while a timing ring
  * is armed (hb_ctx_timing_begin); smaller decodes then report ms_total only. */

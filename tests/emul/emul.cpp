@@ -45,6 +45,9 @@ struct Emul {
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
     hb_tables tbS, tbE; uint32_t maxlen, minlen;
     hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) */
+    bool flat = false;                       /* flat walk (EP-table) on all tiles but the last */
+    std::vector<uint32_t> eptab; uint32_t ep_wf = 10;   /* plain EP-table */
+    uint64_t flat_tiles = 0;
     hb_fsm fsm; bool have_fsm = false; int sync_mode = 0;   /* 0 probe, 1 transducer on full tiles, 2 both + compare */
     uint64_t fsm_tiles = 0, fsm_mismatch = 0;
     std::vector<uint16_t> subs;
@@ -329,6 +332,69 @@ struct Emul {
             if (before[t] != subs[(size_t)tile * T + t]) st.probes_fix += hb_sub_count(subs[(size_t)tile * T + t]);
     }
 
+    /* mirrors hb_emitf_kernel, one full tile that is not the last one */
+    struct ColVec {
+        const uint32_t *w; uint32_t n, k;
+        uint32_t next() { return k < n ? w[k++] : (k++, 0xdeadbeefu); }
+    };
+    bool emit_tile_flat(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes) {
+        constexpr uint32_t LA = 6;
+        const uint64_t B = tile_base[tile];
+        uint32_t o_acc = 0;
+        std::vector<uint32_t> off(T), cnt(T);
+        for (int t = 0; t < T; t++) { off[t] = o_acc; cnt[t] = hb_sub_count(subs[(uint64_t)tile * T + t]); o_acc += cnt[t]; }
+        const uint32_t nk = o_acc;
+        if (B + nk > out_capacity) return false;
+        hb_ptab tb{eptab.data(), 0u, 3u, ((1u << ep_wf) - 1u) << 3, tbE.slow};
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+            std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
+            uint32_t hi_b = nk;
+            struct Fin { uint8_t *at; uint32_t w; };
+            std::vector<Fin> fins;
+            for (int t = 0; t < T; t++) {
+                const uint32_t o = off[t], c = cnt[t];
+                const bool mine = c && o >= wb && o - wb < win;
+                if (!mine) continue;
+                const uint32_t e = hb_sub_entry(subs[(uint64_t)tile * T + t]);
+                if (al + (o - wb) + c + 3 + 8 > stage_bytes) return false;      /* staging bound violated */
+                uint32_t w[WPT + LA];
+                for (uint32_t j = 0; j < WPT + LA; j++) {
+                    const uint64_t i = (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT + j;
+                    w[j] = i < nwords ? words[i] : 0u;
+                }
+                ColVec col{w, WPT + LA, 0};
+                uint8_t *dst = s_out.data() + al + (o - wb);
+                const uint32_t mis = (al + (o - wb)) & 3u;
+                uint8_t *wend = s_out.data() + ((al + (o - wb) + c + 3u) & ~3u);
+                uint32_t fin = ep_wf <= 10 ? hb_emit_flat<3>(tb, col, e, dst, mis, wend)
+                                           : hb_emit_flat<2>(tb, col, e, dst, mis, wend);
+                if (col.k > WPT + LA) return false;                          /* read past the look-ahead rows */
+                fins.push_back(Fin{wend - 4, fin});
+                st.probes_emit += c;
+                if (o + c - wb >= win && o + c < nk) hi_b = o + c;
+            }
+            /* worst store order: every slice's first word lands last (zeros below its first
+             * byte) ... then the barrier, then the final words once more */
+            for (int t = 0; t < T; t++) {
+                const uint32_t o = off[t], c = cnt[t];
+                if (!(c && o >= wb && o - wb < win)) continue;
+                const uint32_t a0 = al + (o - wb);
+                for (uint32_t i = a0 & ~3u; i < a0; i++) s_out[i] = 0;
+            }
+            for (const Fin &f : fins) for (int i = 0; i < 4; i++) f.at[i] = (uint8_t)(f.w >> (8 * i));
+            if (lo_b < hi_b) {
+                uint8_t *gbase = out + B + wb - al;
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                for (uint32_t i = begb; i < endb; i++) gbase[i] = s_out[i];
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+        }
+        flat_tiles++;
+        return true;
+    }
+
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
     bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
                    uint64_t total_valid) {
@@ -407,9 +473,10 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, uint32_t wf64) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, uint32_t wf64, uint32_t ep_wf) {
     Emul<WPT, T> E;
-    E.emit_mode = emit_mode;
+    E.emit_mode = emit_mode == 2 ? 1 : emit_mode;
+    E.flat = emit_mode == 2 && WPT >= 4;
     E.sync_mode = sync_mode;
     E.have_fsm = fsm_states != 0;
     E.fsm = hb_fsm{fsm_tab, 0u, fsm_depth, fsm_pstep};
@@ -439,8 +506,17 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
         uint32_t win = emit_win ? emit_win : ((T * max_c + 15u) & ~15u);   /* 0 = worst case, one window */
         if (win < ((max_c + 15u) & ~15u)) win = (max_c + 15u) & ~15u;      /* a window holds at least one thread's output */
         uint32_t stage = (win + max_c + 16u + 15u) & ~15u;
-        for (uint32_t tile = 0; tile < E.ntiles; tile++)
-            if (!E.emit_tile(tile, out, out_capacity, win, stage, res[0])) { rc = -6; break; }
+        if (E.flat) {   /* EP-table exactly as the kernel builds it */
+            E.ep_wf = ep_wf ? ep_wf : 10u;
+            E.eptab.resize((size_t)2 << E.ep_wf);
+            for (uint32_t x = 0; x < (1u << E.ep_wf); x++) hb_ep_entry(slow, x, E.ep_wf, &E.eptab[2 * x], &E.eptab[2 * x + 1]);
+        }
+        for (uint32_t tile = 0; tile < E.ntiles; tile++) {
+            const bool flat = E.flat && tile + 1 < E.ntiles;
+            if (flat ? !E.emit_tile_flat(tile, out, out_capacity, win, stage + 16)
+                     : !E.emit_tile(tile, out, out_capacity, win, stage, res[0])) { rc = -6; break; }
+        }
+        if (E.flat && E.ntiles > 1 && E.flat_tiles != E.ntiles - 1) rc = -103;
         if (result) memcpy(result, res, sizeof(res));
     }
     if (E.st.long_probes >> 63) rc = -100;   /* fast and slow word walks disagreed */
@@ -458,13 +534,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
                         const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
-                        const uint32_t *e64, uint32_t wf64) {
+                        const uint32_t *e64, uint32_t wf64, uint32_t ep_wf) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep, emit_mode, e64, wf64)
+                          fsm_depth, fsm_pstep, emit_mode, e64, wf64, ep_wf)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

@@ -43,7 +43,7 @@ def lib():
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                C.c_void_p, C.POINTER(Stats), C.c_uint32,
                                C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_int, C.c_void_p, C.c_uint32]
+                               C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
 
@@ -57,12 +57,13 @@ def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
 
 
 def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=True,
-        out_capacity=None, out_offset=0, emit_win=0, sync_mode=2, emit_mode=1):
+        out_capacity=None, out_offset=0, emit_win=0, sync_mode=2, emit_mode=1, ep_wf=10):
     """Returns (out bytes, shard_map[32], result[4], stats dict, rc).
     sync_mode: 0 = probe sync kernel only, 1 = transducer kernel on full tiles (the
     product's default dispatch), 2 = both, failing (rc -101) unless they agree.
     emit_mode: 0 = byte-store emit walk, 1 = word-store walk (WPT >= 2; narrower test
-    shapes fall back to bytes)."""
+    shapes fall back to bytes), 2 = flat walk (EP-table of ep_wf index bits) on every tile
+    but the last one (wpt >= 4), word-store walk on the last."""
     cap = int(out_capacity if out_capacity is not None else bits_own + 64)
     raw = np.zeros(cap + 64 + out_offset, dtype=np.uint8)
     out = raw[out_offset:]
@@ -82,7 +83,7 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
                         out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win,
                         sync_mode, lut["fsm_states"], fsm.ctypes.data, fdepth.ctypes.data,
-                        fpstep.ctypes.data, emit_mode, e64.ctypes.data, lut["wf64"])
+                        fpstep.ctypes.data, emit_mode, e64.ctypes.data, lut["wf64"], ep_wf)
     return out, smap, res, st.as_dict(), rc
 
 

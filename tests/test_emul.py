@@ -391,3 +391,67 @@ def test_random_codes_and_streams(seed):
         assert rc == 0 and int(res[0]) == n, tag
         assert np.array_equal(out[:n], want), tag
         assert not out[n:].any(), tag
+
+
+# ---- flat emit walk (hb_emit_flat / hb_emitf_kernel) -----------------------------------
+
+@pytest.mark.parametrize("ep_wf", [8, 10, 11, 12])
+@pytest.mark.parametrize("shape", [(8, 256), (4, 32), (16, 256)])
+@pytest.mark.parametrize("name", ["paper1", "book2", "world192", "ecoli", "kjv"])
+def test_flat_emit_corpora(name, shape, ep_wf):
+    """flat walk over every tile but the last: whole staging words only, final word repaired
+    after the barrier; every output alignment"""
+    st = _stream(name)
+    if name in ("kjv", "book2") and (shape != (8, 256) or ep_wf != 10):
+        pytest.skip("large corpus: product shape only")
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    for off in ((0, 1, 2, 3, 7, 13) if name == "paper1" else (0, 5)):
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_mode=2, ep_wf=ep_wf, out_offset=off)
+        assert rc == 0 and int(res[0]) == st.usize
+        assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
+        assert not out[st.usize:].any()
+
+
+@pytest.mark.parametrize("win", [2048, 1008, 144])
+def test_flat_emit_in_several_windows(win):
+    for name in ("paper1", "ecoli"):
+        st = _stream(name)
+        lut = hb.build_lut(st.tree)
+        w = E.words_of(st.data, st.nbytes)
+        for off in (0, 5):
+            out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, 8, 256, emit_win=win, out_offset=off, emit_mode=2)
+            assert rc == 0 and int(res[0]) == st.usize
+            assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
+            assert not out[st.usize:].any()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flat_emit_random_codes(seed):
+    """random complete trees with codewords of up to 32 bits: the look-ahead rows and the
+    single-symbol fallback of the flat walk"""
+    rng = np.random.default_rng(7000 + seed)
+    for case in range(10):
+        nleaves = int(rng.choice([2, 3, 5, 17, 64, 200, 256]))
+        maxlen = int(rng.choice([4, 9, 13, 20, 32]))
+        lengths = O.random_lengths(rng, nleaves, maxlen)
+        tree, codes = O.tree_from_lengths(lengths)
+        if min(lengths) == max(lengths):
+            continue
+        wts = np.array([2.0 ** (-l) for l in lengths])
+        mode = int(rng.integers(3))
+        p = np.ones(len(lengths)) if mode == 0 else (wts if mode == 1 else 1.0 / wts)
+        n = int(rng.choice([3000, 20000, 60000]))
+        syms = rng.choice(len(lengths), size=n, p=p / p.sum())
+        data, bits = O.encode_with_codes(codes, syms)
+        st = O.Stream(tree, data, bits, n)
+        want = (syms & 255).astype(np.uint8)
+        shape = [(8, 256), (4, 32), (8, 256)][int(rng.integers(3))]
+        lut = hb.build_lut(tree)
+        wds = E.words_of(st.data, (bits + 7) // 8)
+        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=2, ep_wf=int(rng.choice([8, 10, 11])),
+                                   out_offset=int(rng.integers(16)))
+        tag = (seed, case, nleaves, maxlen, n, shape)
+        assert rc == 0 and int(res[0]) == n, tag
+        assert np.array_equal(out[:n], want), tag
+        assert not out[n:].any(), tag

@@ -329,7 +329,7 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto"):
+    for path in ("words", "bytes", "auto", "flat"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         c.set_emit_path(path)
         cb = hb.Codebook(c, f.tree)
@@ -376,3 +376,22 @@ def test_tree_with_more_than_256_internal_nodes(ctx, dev):
     got, res, _ = _decode_dev(ctx, cb, f, dev)
     assert res["n_symbols"] == syms.size and np.array_equal(got, (syms & 255).astype(np.uint8))
     cb.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [(0, -1), (8, 4), (10, 4), (11, 3), (12, 2), (12, 0), (9, 1)])
+@pytest.mark.parametrize("name", ["paper1", "world192", "kjv", "ecoli", "bible"])
+def test_flat_emit_table_geometries(dev, name, geom):
+    """hb_emitf_kernel with every EP-table shape (index bits, log2 copies): same bytes, at
+    several output alignments; nothing written outside the slice"""
+    f = _stream(name)
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    c.set_emit_path("flat")
+    c.set_emit_table(*geom)
+    cb = hb.Codebook(c, f.tree)
+    for off in (0, 1, 6, 11):
+        got, res, raw = _decode_dev(c, cb, f, dev, out_offset=off)
+        assert res["n_symbols"] == f.usize and O.sha256(got) == O.CORPORA[name][2], (geom, off)
+        assert not raw[off + f.usize:].any() and not raw[:off].any()
+    cb.close()
+    c.close()
