@@ -45,6 +45,12 @@ class Result(C.Structure):
                 ("ms_scan", C.c_float), ("ms_emit", C.c_float)]
 
 
+class MultiResult(C.Structure):
+    _fields_ = [("n_symbols", C.c_uint64), ("n_devices", C.c_int32), ("launches", C.c_uint32),
+                ("ms_device_max", C.c_float), ("ms_wall", C.c_float),
+                ("shard_symbols", C.c_uint64 * 8), ("shard_ms", C.c_float * 8)]
+
+
 class HuffFileC(C.Structure):
     _fields_ = [("nodes", C.c_int32), ("wide", C.c_int32), ("bits", C.c_uint64),
                 ("usize", C.c_uint64), ("tree", C.POINTER(Node)),
@@ -120,6 +126,22 @@ def lib():
     L.hb_codebook_destroy.restype = None
     L.hb_codebook_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.hb_decode_device.argtypes = [vp, vp, vp, u64, u64, vp, u64, C.POINTER(Result)]
+    L.hb_multi_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.hb_multi_destroy.argtypes = [vp]
+    L.hb_multi_destroy.restype = None
+    L.hb_multi_devices.argtypes = [vp]
+    L.hb_multi_last_error.argtypes = [vp]
+    L.hb_multi_last_error.restype = C.c_char_p
+    L.hb_multi_load.argtypes = [vp, vp, i32, vp, u64]
+    L.hb_multi_generate.argtypes = [vp, i32, u64, u64, C.POINTER(u64)]
+    L.hb_multi_decode.argtypes = [vp, C.POINTER(MultiResult)]
+    L.hb_multi_download.argtypes = [vp, vp, u64]
+    L.hb_multi_verify.argtypes = [vp, i32, u64, C.POINTER(u64)]
+    L.hb_multi_decode_host.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(MultiResult)]
+    L.hb_host_pin.argtypes = [vp, u64]
+    L.hb_host_unpin.argtypes = [vp]
+    L.hb_shard_result.argtypes = [vp, C.POINTER(Result)]
+    L.hb_decode_onethread.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
     L.hb_shard_map.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.hb_shard_compose.argtypes = [vp, vp, i32, i32, vp]
     L.hb_shard_emit.argtypes = [vp, vp, vp, u64, u64, u64, vp, vp, u64, C.POINTER(Result)]
@@ -320,6 +342,10 @@ class Context:
 
     def close(self):
         if self.h:
+            # a codebook must not outlive its context (hb_codebook_destroy uses the context's
+            # device and stream): close the ones still open first
+            for cb in list(getattr(self, "_codebooks", ())):
+                cb.close()
             lib().hb_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -340,6 +366,9 @@ class Codebook:
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         lib().hb_codebook_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         self.maxlen, self.minlen, self.w1, self.n_entries = a.value, b.value, c.value, d.value
+        if not hasattr(ctx, "_codebooks"):
+            ctx._codebooks = []
+        ctx._codebooks.append(self)
 
     def table(self, which):
         """Device-resident code table copied back to the host: "lut", "stab", "etab", "e64"
@@ -353,8 +382,11 @@ class Codebook:
 
     def close(self):
         if self.h:
-            lib().hb_codebook_destroy(self.h)
+            if self.ctx.h:   # after Context.close() the library has already released it
+                lib().hb_codebook_destroy(self.h)
             self.h = C.c_void_p()
+            if self in getattr(self.ctx, "_codebooks", ()):
+                self.ctx._codebooks.remove(self)
 
     def __del__(self):
         try:
@@ -436,3 +468,82 @@ def gen_verify_device(ctx: Context, model: Model, seed: int, first: int, n: int,
     _check(lib().hb_gen_verify_device(ctx.h, C.byref(model.c), seed, first, n, d_out, C.byref(bad)),
            "hb_gen_verify_device", ctx.h)
     return bad.value
+
+
+# ---- one process, N devices -----------------------------------------------------------
+
+def _multi_dict(r: MultiResult):
+    n = r.n_devices
+    return {"n_symbols": r.n_symbols, "n_devices": n, "launches": r.launches,
+            "ms_device_max": r.ms_device_max, "ms_wall": r.ms_wall,
+            "shard_symbols": list(r.shard_symbols[:n]), "shard_ms": list(r.shard_ms[:n])}
+
+
+class Multi:
+    """hb_multi_*: one stream over several GPUs of this process (byte-range shards, maps
+    exchanged by peer copies)."""
+
+    def __init__(self, n_devices=0, devices=None):
+        self.h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            n_devices = len(devices)
+        _check(lib().hb_multi_create(arr, n_devices, C.byref(self.h)), "hb_multi_create")
+        self.n = lib().hb_multi_devices(self.h)
+
+    def _ck(self, rc, where):
+        if rc != 0:
+            raise HuffError(rc, where, lib().hb_multi_last_error(self.h).decode())
+
+    def decode_host(self, tree, data, bits, out):
+        tree = np.ascontiguousarray(tree)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        r = MultiResult()
+        self._ck(lib().hb_multi_decode_host(self.h, tree.ctypes.data, len(tree), data.ctypes.data, bits,
+                                            out.ctypes.data, out.size, C.byref(r)), "hb_multi_decode_host")
+        return _multi_dict(r)
+
+    def load(self, tree, data, bits):
+        tree = np.ascontiguousarray(tree)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        self._ck(lib().hb_multi_load(self.h, tree.ctypes.data, len(tree), data.ctypes.data, bits), "hb_multi_load")
+
+    def generate(self, kind, seed, n_symbols):
+        bits = C.c_uint64()
+        self._ck(lib().hb_multi_generate(self.h, kind, seed, n_symbols, C.byref(bits)), "hb_multi_generate")
+        return bits.value
+
+    def decode(self):
+        r = MultiResult()
+        self._ck(lib().hb_multi_decode(self.h, C.byref(r)), "hb_multi_decode")
+        return _multi_dict(r)
+
+    def download(self, out):
+        self._ck(lib().hb_multi_download(self.h, out.ctypes.data, out.size), "hb_multi_download")
+
+    def verify(self, kind, seed):
+        bad = C.c_uint64()
+        self._ck(lib().hb_multi_verify(self.h, kind, seed, C.byref(bad)), "hb_multi_verify")
+        return bad.value
+
+    def close(self):
+        if self.h:
+            lib().hb_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_onethread(ctx: Context, tree, data, bits: int, out: np.ndarray):
+    """the reference's onethread approach: the whole stream on one device thread (debug aid)"""
+    tree = np.ascontiguousarray(tree)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    r = Result()
+    _check(lib().hb_decode_onethread(ctx.h, tree.ctypes.data, len(tree), data.ctypes.data, bits,
+                                     out.ctypes.data, out.size, C.byref(r)), "hb_decode_onethread", ctx.h)
+    return _res_dict(r)

@@ -817,6 +817,36 @@ extern "C" int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_c
     return HB_OK;
 }
 
+extern "C" int hb_shard_result(hb_ctx *ctx, hb_result *res) {
+    if (!ctx || !res) return HB_ERR_ARG;
+    if (!ctx->have_map) return HB_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->map_ntiles == 0) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        memset(res, 0, sizeof(*res));
+        return HB_OK;
+    }
+    return finish_result(ctx, ctx->map_ntiles, ctx->last_launches, res);
+}
+
+extern "C" int hb_host_pin(const void *ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return HB_ERR_ARG;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return HB_OK;
+    cudaGetLastError();
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return HB_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return HB_ERR_CUDA; }
+    return HB_OK;
+}
+
+extern "C" int hb_host_unpin(const void *ptr) {
+    if (!ptr) return HB_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+    cudaGetLastError();
+    return e == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
 extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                                 uint64_t comp_bytes, uint64_t bits, void *d_out,
                                 uint64_t out_capacity, hb_result *res) {
@@ -989,6 +1019,76 @@ extern "C" int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
         }
     } while (0);
     return rc;
+}
+
+/* ---- onethread: the whole stream on ONE device thread (debug aid) ------------------
+ * The reference registers a `<<<1,1>>>` serial tree walk as its "onethread" approach
+ * (framework/onethread.cu:13-52; the loop of simpleDecode, framework/mainrun.c:38-55).
+ * Same thing here over the uploaded node array: a device-side statement of the stream
+ * semantics that shares nothing with the table-driven kernels -- useful to tell a table
+ * bug from a data bug.  Not a fast path. */
+__global__ void hb_onethread_kernel(const hb_node_abi *__restrict__ tree, const uint8_t *__restrict__ data,
+                                    uint64_t bits, uint8_t *__restrict__ out, uint64_t out_capacity,
+                                    uint64_t *__restrict__ n_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int32_t node = 0;
+    uint64_t n = 0;
+    bool full = false;
+    for (uint64_t pos = 0; pos < bits; pos++) {
+        const uint32_t bit = (data[pos >> 3] >> (pos & 7)) & 1u;
+        node = bit ? tree[node].ione : tree[node].izero;
+        if (tree[node].izero == -1 && tree[node].ione == -1) {
+            if (n < out_capacity) out[n] = tree[node].sym; else full = true;
+            n++;
+            node = 0;
+        }
+    }
+    n_out[0] = n;
+    n_out[1] = full ? 1u : 0u;
+}
+
+extern "C" int hb_decode_onethread(hb_ctx *ctx, const hb_node_abi *tree, int nodes, const uint8_t *data,
+                                   uint64_t bits, uint8_t *out, uint64_t out_capacity, hb_result *res) {
+    if (!ctx || !tree || nodes < 1 || (!data && bits) || (!out && out_capacity)) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < nodes; i++) {   /* the walk indexes the array with these: keep them inside it */
+        const int32_t z = tree[i].izero, o = tree[i].ione;
+        if ((z == -1) != (o == -1) || z < -1 || o < -1 || z >= nodes || o >= nodes) return HB_ERR_TREE;
+    }
+    if (tree[0].izero == -1) return HB_ERR_TREE;
+    const uint64_t nbytes = (bits + 7) / 8;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_comp, nbytes + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) return rc;
+    hb_node_abi *d_tree = nullptr;
+    uint64_t *d_n = nullptr;
+    CK(cudaMallocAsync((void **)&d_tree, sizeof(hb_node_abi) * (size_t)nodes + 16, ctx->stream));
+    CK(cudaMallocAsync((void **)&d_n, 2 * sizeof(uint64_t), ctx->stream));
+    CK(cudaMemcpyAsync(d_tree, tree, sizeof(hb_node_abi) * (size_t)nodes, cudaMemcpyHostToDevice, ctx->stream));
+    if (nbytes) CK(cudaMemcpyAsync(ctx->d_comp.p, data, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev0[0], ctx->stream));
+    hb_onethread_kernel<<<1, 1, 0, ctx->stream>>>(d_tree, (const uint8_t *)ctx->d_comp.p, bits,
+                                                  (uint8_t *)ctx->d_out.p, out_capacity, d_n);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev0[4], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_res, d_n, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t n = ctx->h_res[0];
+    const bool full = ctx->h_res[1] != 0;
+    if (n && !full) {
+        CK(cudaMemcpyAsync(out, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaFreeAsync(d_tree, ctx->stream));
+    CK(cudaFreeAsync(d_n, ctx->stream));
+    if (res) {
+        memset(res, 0, sizeof(*res));
+        res->n_symbols = full ? out_capacity : n;
+        res->launches = 1;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev0[0], ctx->ev0[4]) == cudaSuccess) res->ms_total = ms;
+    }
+    return full ? HB_ERR_OUTPUT_FULL : HB_OK;
 }
 
 /* used by hb_gen.cu (setup-only generator) to run on the context's device/stream */

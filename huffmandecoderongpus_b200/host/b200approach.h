@@ -29,6 +29,19 @@ void b200Approach(struct CompressedData *cd, struct UnCompressedData *uncompress
 void b200ApproachL(struct CompressedDataL *cd, struct UnCompressedDataL *uncompressed,
                    void *paramdata);
 
+/* The same stream over several GPUs of this process (byte-range shards, maps exchanged by
+ * peer copies; include/huffb200.h hb_multi_*).  paramdata: int * = number of devices, NULL =
+ * the B200_DEVICES environment variable, else every visible device.  Registered next to
+ * b200Approach: newDecoder(b200ApproachMulti, &ndev, "b200multi"). */
+void b200ApproachMulti(struct CompressedData *cd, struct UnCompressedData *uncompressed,
+                       void *paramdata);
+void b200ApproachMultiL(struct CompressedDataL *cd, struct UnCompressedDataL *uncompressed,
+                        void *paramdata);
+
+/* the reference's debug approach of that name (framework/onethread.cu:33-52, registered at
+ * framework/mainrun.c:480): the whole stream on one device thread */
+void onethreadApproach(struct CompressedData *cd, struct UnCompressedData *uncompressed, void *paramdata);
+
 /* device milliseconds (CUDA events, kernels only) of the last call, and the
  * number of symbols it produced */
 double b200ApproachLastDeviceMs(void);

@@ -10,7 +10,10 @@
  *
  *   HuffFramework <test> [files-dir]
  *   tests: hello paper1 news book2 kjv ecoli world192 bible bigtable all
- *          quickgraph graph synth1g synthfib
+ *          quickgraph1..3 graph1..4 (the reference's names, framework/mainrun.c:590-616;
+ *          quickgraph / graph = the GPU ones, quickgraph2 / graph2) kjvprof opt bts
+ *          multi (every corpus through b200ApproachMulti) onethread
+ *          synth1g synthfib synth16g (B200_DEVICES=N: one stream over N GPUs)
  *
  * The GPU approach (b200Approach) is always registered.  The CPU baselines
  * (the oracle's restatement of simpleDecode / jumptableApproach) are only
@@ -119,9 +122,47 @@ static void graphtest(struct decoder *d, struct dataset *s, int incs) {
     }
 }
 
+/* BASELINE.json configs 4/5 over N GPUs of this process (B200_DEVICES=N): ONE stream, built
+ * with the bundled generator, cut into byte-range shards, decoded resident (hb_multi_*),
+ * every output slice verified on its device */
+static void synth_multi(int kind, unsigned log2n, const char *label, int ndev) {
+    hb_multi *m = NULL;
+    int rc = hb_multi_create(NULL, ndev, &m);
+    if (rc) { printf("hb_multi_create(%d): %s\n", ndev, hb_strerror(rc)); exit(-1); }
+    const uint64_t n = 1ull << log2n, seed = 0x48554646ull;
+    uint64_t bits = 0, bad = 0;
+    if ((rc = hb_multi_generate(m, kind, seed, n, &bits))) {
+        printf("hb_multi_generate: %s (%s)\n", hb_strerror(rc), hb_multi_last_error(m));
+        exit(-1);
+    }
+    hb_multi_result res, best;
+    memset(&best, 0, sizeof(best));
+    for (int i = 0; i < 5; i++) {
+        if ((rc = hb_multi_decode(m, &res))) {
+            printf("hb_multi_decode: %s (%s)\n", hb_strerror(rc), hb_multi_last_error(m));
+            exit(-1);
+        }
+        if (i == 0 || res.ms_device_max < best.ms_device_max) best = res;
+    }
+    if ((rc = hb_multi_verify(m, kind, seed, &bad))) { printf("hb_multi_verify: %s\n", hb_strerror(rc)); exit(-1); }
+    const double ms = best.ms_device_max;
+    printf("%17s %8s  %2d %.9f ms   | %.3f GB/s out, %.3f GB/s in (device, max over %d GPUs; wall %.3f ms), "
+           "bits %llu, symbols %llu, mismatches %llu\n", "b200multi", label, best.n_devices, ms,
+           (double)n / (ms * 1e-3) / 1e9, (double)((bits + 7) / 8) / (ms * 1e-3) / 1e9, best.n_devices,
+           best.ms_wall, (unsigned long long)bits, (unsigned long long)best.n_symbols, (unsigned long long)bad);
+    for (int i = 0; i < best.n_devices; i++)
+        printf("%17s shard %d: %llu symbols, %.4f ms\n", "", i, (unsigned long long)best.shard_symbols[i], best.shard_ms[i]);
+    if (bad || best.n_symbols != n) { fprintf(stderr, "problem with : b200multi\n"); exit(1); }
+    hb_multi_destroy(m);
+}
+
 /* BASELINE.json configs 4/5 from the C side: build the stream on the device with
  * the bundled generator, decode it resident, verify every byte on the device */
 static void synth(int kind, unsigned log2n, const char *label) {
+    if (getenv("B200_DEVICES") && atoi(getenv("B200_DEVICES")) > 0) {
+        synth_multi(kind, log2n, label, atoi(getenv("B200_DEVICES")));
+        return;
+    }
     hb_ctx *ctx = NULL;
     hb_model *m = (hb_model *)malloc(sizeof(*m));
     int rc = hb_ctx_create(0, NULL, &ctx);
@@ -165,6 +206,12 @@ int main(int argc, char *argv[]) {
     fprintf(stderr, "running test: %s\n", testname);
 
     struct decoder *b200 = newDecoder(b200Approach, NULL, "b200");
+    /* the multi-GPU approach takes its device count the way jumptable takes jumpbits
+     * (framework/mainrun.c:442,500-501); 0 = every visible device */
+    static int ndev = 0;
+    if (getenv("B200_DEVICES")) ndev = atoi(getenv("B200_DEVICES"));
+    struct decoder *b200multi = newDecoder(b200ApproachMulti, &ndev, "b200multi");
+    struct decoder *onethread = newDecoder(onethreadApproach, NULL, "onethread");
 #ifdef WITH_ORACLE_BASELINES
     static int jumpbits = 8;
     struct decoder *simpledec = newDecoder(simpleDecode, NULL, "simpleDecode");
@@ -172,7 +219,7 @@ int main(int argc, char *argv[]) {
     /* the reference's remaining CPU approaches (framework/mainrun.c:
      * 496-501), taken UNMODIFIED from oracle/_ref/libref.so (make -C oracle ref) when that
      * library is present: same struct layout, same approach signature */
-    struct decoder *refdec[5] = { NULL, NULL, NULL, NULL, NULL };
+    struct decoder *refdec[5] = { NULL, NULL, NULL, NULL, NULL }, *refpes = NULL;
     int nref = 0;
     {
         const char *lib = getenv("HB_REF_LIB") ? getenv("HB_REF_LIB") : "../../oracle/_ref/libref.so";
@@ -186,6 +233,9 @@ int main(int argc, char *argv[]) {
             if (f) refdec[nref++] = newDecoder((void (*)(struct CompressedData *, struct UnCompressedData *, void *))f,
                                                i >= 3 ? &jumpbits : NULL, labels[i]);
         }
+        if (h && dlsym(h, "pesApproach"))
+            refpes = newDecoder((void (*)(struct CompressedData *, struct UnCompressedData *, void *))dlsym(h, "pesApproach"),
+                                NULL, "ref:pes");
         if (!h) fprintf(stderr, "(no %s: reference CPU approaches not listed)\n", lib);
     }
 #endif
@@ -198,10 +248,36 @@ int main(int argc, char *argv[]) {
     if (!strcmp(testname, "bigtable")) { suite = suite_bigtable; ns = 5; }
     else if (!strcmp(testname, "all")) { suite = suite_all; ns = 8; }
     else if (get_set(testname)) { one[0] = testname; suite = one; ns = 1; }
-    else if (!strcmp(testname, "quickgraph")) { graphtest(b200, get_set("paper1"), 10000); }
-    else if (!strcmp(testname, "graph")) { graphtest(b200, get_set("kjv"), 500000); }
+    /* the reference's sweeps (framework/mainrun.c:590-616): 2 = the GPU approach, 1 = the serial
+     * decoder, 3 = decodeBigtableMultiSym, 4 = pes; the CPU ones need HuffFrameworkBaselines */
+    else if (!strcmp(testname, "quickgraph") || !strcmp(testname, "quickgraph2")) { graphtest(b200, get_set("paper1"), 10000); }
+    else if (!strcmp(testname, "graph") || !strcmp(testname, "graph2")) { graphtest(b200, get_set("kjv"), 500000); }
+    else if (!strcmp(testname, "kjvprof")) { evalandshow(b200, get_set("kjv"), 1); }   /* one approach, one corpus: run it under a profiler */
+    else if (!strcmp(testname, "opt")) { evalandshow(b200, get_set("kjv"), 1); evalandshow(b200multi, get_set("kjv"), 1); }
+    else if (!strcmp(testname, "onethread")) { evalandshow(onethread, get_set("hello"), 1); evalandshow(onethread, get_set("paper1"), 1); }
+    else if (!strcmp(testname, "multi")) {
+        for (int i = 0; i < 8; i++) evalandshow(b200multi, get_set(suite_all[i]), 1);
+    }
+#ifdef WITH_ORACLE_BASELINES
+    else if (!strcmp(testname, "quickgraph1")) { graphtest(simpledec, get_set("paper1"), 10000); }
+    else if (!strcmp(testname, "graph1")) { graphtest(simpledec, get_set("kjv"), 500000); }
+    else if (!strcmp(testname, "quickgraph3") && nref > 1) { graphtest(refdec[1], get_set("paper1"), 10000); }
+    else if (!strcmp(testname, "graph3") && nref > 1) { graphtest(refdec[1], get_set("kjv"), 500000); }
+    else if (!strcmp(testname, "graph4") && refpes) { graphtest(refpes, get_set("kjv"), 500000); }
+    else if (!strcmp(testname, "bts") && nref > 2) {
+        for (int i = 0; i < 5; i++) evalandshow(refdec[2], get_set(suite_bigtable[i]), 1);
+    }
+#else
+    else if (!strcmp(testname, "quickgraph1") || !strcmp(testname, "quickgraph3") || !strcmp(testname, "graph1") ||
+             !strcmp(testname, "graph3") || !strcmp(testname, "graph4") || !strcmp(testname, "bts")) {
+        fprintf(stderr, "error exit: %s sweeps a CPU approach; this binary has no CPU decode path "
+                        "(build and run HuffFrameworkBaselines)\n", testname);
+        return 1;
+    }
+#endif
     else if (!strcmp(testname, "synth1g")) { synth(HB_MODEL_ENGLISH, 30, "synth1g"); }
     else if (!strcmp(testname, "synthfib")) { synth(HB_MODEL_FIBONACCI, 32, "synthfib"); }
+    else if (!strcmp(testname, "synth16g")) { synth(HB_MODEL_FIBONACCI, 34, "synth16g"); }   /* BASELINE config 5 at its stated size */
     else { fprintf(stderr, "error exit: unknown test %s\n", testname); return 1; }
 
     if (suite) {
@@ -216,7 +292,10 @@ int main(int argc, char *argv[]) {
     }
     for (int i = 0; i < NSETS; i++) freeTestData(g_sets[i].td);
     freeDecoder(b200);
+    freeDecoder(b200multi);
+    freeDecoder(onethread);
 #ifdef WITH_ORACLE_BASELINES
+    if (refpes) freeDecoder(refpes);
     freeDecoder(simpledec);
     freeDecoder(jumptable);
     for (int k = 0; k < nref; k++) freeDecoder(refdec[k]);

@@ -185,12 +185,60 @@ int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                   const uint64_t *d_entry_base, void *d_out,
                   uint64_t out_capacity, hb_result *res);
 
+/* Result of the last hb_shard_emit on this context (synchronises its stream): for callers
+ * that queued the emit with res == NULL to keep several devices busy at once. */
+int hb_shard_result(hb_ctx *ctx, hb_result *res);
+
+/* ---- one process, N devices ---------------------------
+ * The stream is cut into byte-range shards, one per device; the 32-entry shard maps travel by
+ * peer copies ordered with events (256 B each; no NCCL, no host round trip), every device
+ * composes the maps to its left and emits its shard into its own output slice.
+ * devices == NULL: devices 0 .. n_devices-1; n_devices <= 0: all visible devices. */
+#define HB_MULTI_MAX 8
+typedef struct hb_multi hb_multi;
+typedef struct hb_multi_result {
+    uint64_t n_symbols;                   /* whole stream */
+    int32_t  n_devices;                   /* shards actually used (tiny streams use fewer devices) */
+    uint32_t launches;                    /* kernels launched on all devices */
+    float    ms_device_max;               /* max over devices of the CUDA-event time map .. emit */
+    float    ms_wall;                     /* host wall clock of the call */
+    uint64_t shard_symbols[HB_MULTI_MAX];
+    float    shard_ms[HB_MULTI_MAX];
+} hb_multi_result;
+int  hb_multi_create(const int *devices, int n_devices, hb_multi **m);
+void hb_multi_destroy(hb_multi *m);
+int  hb_multi_devices(const hb_multi *m);
+const char *hb_multi_last_error(const hb_multi *m);
+/* resident: shard a host stream over the devices (or build a synthetic one on them with the
+ * bundled generator), then decode as often as wanted; device-timed */
+int  hb_multi_load(hb_multi *m, const hb_node_abi *tree, int nodes, const uint8_t *data, uint64_t bits);
+int  hb_multi_generate(hb_multi *m, int model_kind, uint64_t seed, uint64_t n_symbols, uint64_t *bits_out);
+int  hb_multi_decode(hb_multi *m, hb_multi_result *res);
+int  hb_multi_download(hb_multi *m, uint8_t *out, uint64_t out_capacity);
+/* every output slice against regenerated symbols (streams made by hb_multi_generate) */
+int  hb_multi_verify(hb_multi *m, int model_kind, uint64_t seed, uint64_t *mismatches);
+/* host buffers in and out: upload, decode, download (what b200ApproachMulti calls) */
+int  hb_multi_decode_host(hb_multi *m, const hb_node_abi *tree, int nodes, const uint8_t *data,
+                          uint64_t bits, uint8_t *out, uint64_t out_capacity, hb_multi_result *res);
+
+/* Page-lock / release a caller-owned host range (cudaHostRegister, portable) so that the
+ * copies of hb_decode_host / hb_multi_decode_host are true DMA transfers that overlap across
+ * devices.  Ranges that are already page-locked are accepted (HB_OK).  Optional. */
+int  hb_host_pin(const void *ptr, uint64_t bytes);
+int  hb_host_unpin(const void *ptr);
+
 /* ---- host buffers (what the approach call does) --------------------------- */
 /* Upload tree + data, decode, download.  data must have >= ceil(bits/8) bytes.
  * Device buffers are cached in the context and grow on demand. */
 int hb_decode_host(hb_ctx *ctx, const hb_node_abi *tree, int nodes,
                    const uint8_t *data, uint64_t bits, uint8_t *out,
                    uint64_t out_capacity, hb_result *res);
+
+/* The whole stream on ONE device thread: the reference's "onethread" approach
+ * (framework/onethread.cu:13-52), a bit-serial walk of the uploaded node array that shares
+ * nothing with the table-driven kernels.  Debug aid (seconds per 100 MB), host buffers. */
+int hb_decode_onethread(hb_ctx *ctx, const hb_node_abi *tree, int nodes, const uint8_t *data,
+                        uint64_t bits, uint8_t *out, uint64_t out_capacity, hb_result *res);
 
 /* ---- .huff container ------------------------------------------------------ */
 /* "HUFF" (reference framework/huffdata.c:27-68: BE i32 nodes, bits, usize) and
