@@ -141,6 +141,8 @@ def lib():
     L.hb_host_pin.argtypes = [vp, u64]
     L.hb_host_unpin.argtypes = [vp]
     L.hb_shard_result.argtypes = [vp, C.POINTER(Result)]
+    L.hb_shard_map_host.argtypes = [vp, vp, vp, u64, u64, u64, vp]
+    L.hb_shard_emit_host.argtypes = [vp, vp, vp, vp, u64, C.POINTER(Result)]
     L.hb_decode_onethread.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
     L.hb_shard_map.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.hb_shard_compose.argtypes = [vp, vp, i32, i32, vp]
@@ -425,6 +427,18 @@ def shard_emit(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_entry_base, 
                                d_entry_base, d_out, out_capacity,
                                C.byref(r) if want_result else None), "hb_shard_emit", ctx.h)
     return _res_dict(r) if want_result else None
+
+
+def shard_map_host(ctx, cb, h_comp: np.ndarray, comp_bytes, bits_own, bits_avail, d_map):
+    _check(lib().hb_shard_map_host(ctx.h, cb.h, h_comp.ctypes.data, comp_bytes, bits_own, bits_avail, d_map),
+           "hb_shard_map_host", ctx.h)
+
+
+def shard_emit_host(ctx, cb, d_entry_base, h_out: np.ndarray):
+    r = Result()
+    _check(lib().hb_shard_emit_host(ctx.h, cb.h, d_entry_base, h_out.ctypes.data, h_out.size, C.byref(r)),
+           "hb_shard_emit_host", ctx.h)
+    return _res_dict(r)
 
 
 def decode_host(ctx: Context, tree, data, bits: int, out: np.ndarray):

@@ -70,6 +70,7 @@ struct hb_ctx {
     uint64_t pipe_chunk_bytes = 32ull << 20;
     cudaEvent_t pipe_t0 = nullptr, pipe_t1 = nullptr;
     uint64_t *h_res = nullptr; /* pinned, 8 words */
+    uint64_t hs_readable = 0, hs_own = 0, hs_avail = 0;   /* shard of the last hb_shard_map_host */
 };
 
 static const char *const k_errs[] = {
@@ -139,9 +140,14 @@ extern "C" int hb_ctx_create(int device, void *cuda_stream, hb_ctx **out) {
         }
         ctx->own_stream = true;
     }
-    for (int i = 0; i < HB_NEV; i++) cudaEventCreate(&ctx->ev0[i]);
+    int nev = 0;
+    for (; nev < HB_NEV; nev++)
+        if (cudaEventCreate(&ctx->ev0[nev]) != cudaSuccess) break;
     ctx->ev = ctx->ev0;
-    if (cudaMallocHost((void **)&ctx->h_res, 8 * sizeof(uint64_t)) != cudaSuccess) {
+    if (nev < HB_NEV || cudaMallocHost((void **)&ctx->h_res, 8 * sizeof(uint64_t)) != cudaSuccess) {
+        cudaGetLastError();
+        for (int i = 0; i < nev; i++) cudaEventDestroy(ctx->ev0[i]);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return HB_ERR_CUDA;
     }
@@ -406,7 +412,7 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
     if (bits_avail < bits_own) return HB_ERR_ARG;
     if (bits_avail && !d_comp) return HB_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(d_comp) & 15u) != 0) return HB_ERR_ARG;
-    if (comp_bytes < (bits_avail + 7) / 8) return HB_ERR_ARG;
+    if (comp_bytes < bits_avail / 8 + (bits_avail % 8 != 0)) return HB_ERR_ARG;
     const uint64_t tile_bits = (uint64_t)HB_T * 32u * (uint64_t)ctx->wpt;
     uint64_t ntiles = (bits_own + tile_bits - 1) / tile_bits;
     if (ntiles > 0x7fffffffull) return HB_ERR_ARG;
@@ -895,15 +901,23 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
     if (!ctx->s_d2h) CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     if (!ctx->pipe_t0) { CK(cudaEventCreate(&ctx->pipe_t0)); CK(cudaEventCreate(&ctx->pipe_t1)); }
     if (K > ctx->pipe_cap) {
+        /* grow events and pinned words together; pipe_cap only moves once both exist */
         cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->pipe_ev, sizeof(cudaEvent_t) * 2 * (size_t)K);
         if (!ne) return HB_ERR_NOMEM;
         ctx->pipe_ev = ne;
-        for (int i = 2 * ctx->pipe_cap; i < 2 * K; i++)
-            CK(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
-        if (ctx->h_pipe) CK(cudaFreeHost(ctx->h_pipe));
-        ctx->h_pipe = nullptr;
+        uint64_t *nh = nullptr;
+        cudaError_t e = cudaMallocHost((void **)&nh, sizeof(uint64_t) * 36 * (size_t)K);
+        int made = 2 * ctx->pipe_cap;
+        for (; e == cudaSuccess && made < 2 * K; made++)
+            e = cudaEventCreateWithFlags(&ctx->pipe_ev[made], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            for (int i = 2 * ctx->pipe_cap; i < made - 1; i++) cudaEventDestroy(ctx->pipe_ev[i]);
+            if (nh) cudaFreeHost(nh);
+            return cuda_fail(ctx, e, "pipeline setup");
+        }
+        if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+        ctx->h_pipe = nh;
         ctx->pipe_cap = K;
-        CK(cudaMallocHost((void **)&ctx->h_pipe, sizeof(uint64_t) * 36 * (size_t)K));
     }
     if ((rc = ensure(ctx, ctx->d_eb, sizeof(uint64_t) * 4 * (size_t)K))) return rc;
     const uint64_t padded = (nbytes + 15) & ~15ull;
@@ -911,12 +925,14 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
     if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) return rc;
     uint8_t *d_comp = (uint8_t *)ctx->d_comp.p, *d_out = (uint8_t *)ctx->d_out.p;
 
-    /* queue every upload (chunk + 16-byte halo), one event each */
+    /* the bytes behind the stream are zero before ANY chunk can read them (a chunk's halo may
+     * reach past the end when the last chunk is shorter than 16 bytes), then every upload
+     * (chunk + 16-byte halo), one event each */
+    CK(cudaMemsetAsync(d_comp + nbytes, 0, padded + 32 - nbytes, ctx->s_h2d));
     for (int k = 0; k < K; k++) {
         const uint64_t a = (uint64_t)k * cbytes;
         const uint64_t b = a + cbytes + 16 < nbytes ? a + cbytes + 16 : nbytes;
         CK(cudaMemcpyAsync(d_comp + a, data + a, b - a, cudaMemcpyHostToDevice, ctx->s_h2d));
-        if (k == K - 1) CK(cudaMemsetAsync(d_comp + nbytes, 0, padded + 32 - nbytes, ctx->s_h2d));
         CK(cudaEventRecord(ctx->pipe_ev[2 * k], ctx->s_h2d));
     }
     CK(cudaEventRecord(ctx->pipe_t0, ctx->stream));
@@ -926,8 +942,10 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
         const uint64_t a = (uint64_t)k * cbytes;
         const bool last = k == K - 1;
         const uint64_t own = last ? bits - 8 * a : 8 * cbytes;
-        const uint64_t avail = last ? own : 8 * (cbytes + 16);
-        const uint64_t readable = last ? padded + 32 - a : cbytes + 16;
+        /* never more valid bits than the stream has: the halo of the last-but-one chunk ends
+         * where the data ends */
+        const uint64_t avail = last ? own : (bits - 8 * a < 8 * (cbytes + 16) ? bits - 8 * a : 8 * (cbytes + 16));
+        const uint64_t readable = last || a + cbytes + 16 > padded + 32 ? padded + 32 - a : cbytes + 16;
         uint64_t *h = ctx->h_pipe + 36 * (size_t)k;
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * k], 0));
         if ((rc = hb_shard_map(ctx, cb, d_comp + a, readable, own, avail, nullptr))) return rc;
@@ -1089,6 +1107,48 @@ extern "C" int hb_decode_onethread(hb_ctx *ctx, const hb_node_abi *tree, int nod
         if (cudaEventElapsedTime(&ms, ctx->ev0[0], ctx->ev0[4]) == cudaSuccess) res->ms_total = ms;
     }
     return full ? HB_ERR_OUTPUT_FULL : HB_OK;
+}
+
+/* ---- rank-local halves of a multi-GPU decode with HOST buffers -----------------------
+ * One process per GPU (torch.distributed, MPI ...): upload + map, the caller exchanges the
+ * 32-entry maps, compose (hb_shard_compose), then emit + download.  The copies are DMA
+ * transfers when the host buffers are page-locked (hb_host_pin). */
+extern "C" int hb_shard_map_host(hb_ctx *ctx, const hb_codebook *cb, const uint8_t *h_comp,
+                                 uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
+                                 uint64_t *d_map) {
+    if (!ctx || !cb || (!h_comp && comp_bytes)) return HB_ERR_ARG;
+    if (comp_bytes < bits_avail / 8 + (bits_avail % 8 != 0)) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t readable = (comp_bytes + 15) / 16 * 16 + 32;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_comp, readable))) return rc;
+    uint8_t *d = (uint8_t *)ctx->d_comp.p;
+    if (comp_bytes) CK(cudaMemcpyAsync(d, h_comp, comp_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d + comp_bytes, 0, readable - comp_bytes, ctx->stream));
+    ctx->hs_readable = readable;
+    ctx->hs_own = bits_own;
+    ctx->hs_avail = bits_avail;
+    return hb_shard_map(ctx, cb, d, readable, bits_own, bits_avail, d_map);
+}
+
+extern "C" int hb_shard_emit_host(hb_ctx *ctx, const hb_codebook *cb, const uint64_t *d_entry_base,
+                                  uint8_t *h_out, uint64_t out_capacity, hb_result *res) {
+    if (!ctx || !cb || (!h_out && out_capacity)) return HB_ERR_ARG;
+    if (!ctx->have_map || !ctx->hs_readable) return HB_ERR_STATE;
+    hb_result local;
+    if (!res) res = &local;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_out, out_capacity + 16))) return rc;
+    rc = hb_shard_emit(ctx, cb, ctx->d_comp.p, ctx->hs_readable, ctx->hs_own, ctx->hs_avail, d_entry_base,
+                       ctx->d_out.p, out_capacity, res);
+    ctx->hs_readable = 0;
+    if (rc) return rc;
+    if (res->n_symbols) {
+        CK(cudaMemcpyAsync(h_out, ctx->d_out.p, res->n_symbols, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return HB_OK;
 }
 
 /* used by hb_gen.cu (setup-only generator) to run on the context's device/stream */

@@ -75,7 +75,13 @@ int hb_huff_load(const char *path, hb_huff_file *out) {
         free(buf);
     }
     {
-        uint64_t nbytes = (out->bits + 7) / 8;
+        /* the header is untrusted: the data bytes it promises must exist in the file before
+         * anything is allocated for them (and bits + 7 must not wrap) */
+        const uint64_t nbytes = out->bits / 8 + (out->bits % 8 != 0);
+        long here = ftell(f), end = -1;
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) end = ftell(f);
+        if (here < 0 || end < here || fseek(f, here, SEEK_SET) != 0) { rc = HB_ERR_IO; goto done; }
+        if (nbytes > (uint64_t)(end - here)) goto done;
         out->data = (uint8_t *)calloc((size_t)nbytes + HB_DATA_PAD, 1);
         if (!out->data) { rc = HB_ERR_NOMEM; goto done; }
         if (nbytes && fread(out->data, 1, (size_t)nbytes, f) != nbytes) goto done;

@@ -24,15 +24,22 @@ static int g_atexit;
 /* evaluate() calls an approach 26 times with the same two buffers (framework/decodeUtil.c:
  * 41-58): page-lock them on first sight, so that the copies are DMA transfers instead of
  * staged pageable copies (and overlap across devices in the multi-GPU approach).  A small
- * cache; a range that overlaps a new one is released first.  B200_PIN=0 turns it off. */
+ * cache; a range that overlaps a new one is released first.
+ * OFF unless the host program asks for it (b200ApproachPinBuffers(1), or B200_PIN=1 in the
+ * environment): a range that stays page-locked after its owner freed it makes any LATER CUDA
+ * copy of the application from memory overlapping it fail, so the program that turns this
+ * on must call b200ApproachReleaseBuffers() before it frees the buffers (host/decodeUtil.c
+ * does, at the end of evaluate()). */
 #define NPINS 4
 static struct { const unsigned char *p; size_t n; unsigned age; } g_pins[NPINS];
 static unsigned g_pin_clock;
+static int g_pin_enabled = -1;
+
+void b200ApproachPinBuffers(int on) { g_pin_enabled = on ? 1 : 0; }
 
 static void pin_range(const void *ptr, size_t n) {
-    static int enabled = -1;
-    if (enabled < 0) { const char *s = getenv("B200_PIN"); enabled = !(s && s[0] == '0'); }
-    if (!enabled || !ptr || n < 4096) return;
+    if (g_pin_enabled < 0) { const char *s = getenv("B200_PIN"); g_pin_enabled = s && s[0] == '1'; }
+    if (!g_pin_enabled || !ptr || n < 4096) return;
     const unsigned char *p = (const unsigned char *)ptr;
     int slot = -1;
     for (int i = 0; i < NPINS; i++) {
@@ -57,6 +64,8 @@ static void unpin_all(void) {
     for (int i = 0; i < NPINS; i++)
         if (g_pins[i].p) { hb_host_unpin(g_pins[i].p); g_pins[i].p = NULL; }
 }
+
+void b200ApproachReleaseBuffers(void) { unpin_all(); }
 
 static void fatal(const char *what, int rc) {
     printf("b200Approach failed in %s: %s (%s)\n", what, hb_strerror(rc),

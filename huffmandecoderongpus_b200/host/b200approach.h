@@ -42,6 +42,13 @@ void b200ApproachMultiL(struct CompressedDataL *cd, struct UnCompressedDataL *un
  * framework/mainrun.c:480): the whole stream on one device thread */
 void onethreadApproach(struct CompressedData *cd, struct UnCompressedData *uncompressed, void *paramdata);
 
+/* Optional: keep the caller's two buffers page-locked across the 26 back-to-back calls of
+ * evaluate() (DMA copies instead of staged pageable ones; kjv 0.6 -> 0.27 ms per call).  A
+ * program that turns this on must call b200ApproachReleaseBuffers() before it frees the
+ * buffers it passed in.  Also enabled by B200_PIN=1 in the environment. */
+void b200ApproachPinBuffers(int on);
+void b200ApproachReleaseBuffers(void);
+
 /* device milliseconds (CUDA events, kernels only) of the last call, and the
  * number of symbols it produced */
 double b200ApproachLastDeviceMs(void);

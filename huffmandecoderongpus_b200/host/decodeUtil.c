@@ -33,7 +33,8 @@ static int repeats(void) {
 struct evalresult evaluate_ex(struct decoder *d, struct TestData *td, int withcheck,
                               const char *want_sha256) {
     struct evalresult r = { 0.0, -1.0, 0 };
-    const int is_b200 = d->decoder_function == (decoder_fn)b200Approach;
+    const int is_b200 = d->decoder_function == (decoder_fn)b200Approach ||
+                        d->decoder_function == (decoder_fn)b200ApproachMulti;
     struct UnCompressedData *out = newUnCompressedData(td->cd->uncompressedsize);
     if (!out) err(1, "out of memory");
     const int n = 1 + repeats();
@@ -66,6 +67,9 @@ struct evalresult evaluate_ex(struct decoder *d, struct TestData *td, int withch
             }
         }
     }
+    /* the approach may have page-locked `out` (b200ApproachPinBuffers): release it before the
+     * memory goes back to the allocator */
+    b200ApproachReleaseBuffers();
     freeUnCompressedData(out);
     return r;
 }

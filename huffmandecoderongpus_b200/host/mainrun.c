@@ -205,6 +205,9 @@ int main(int argc, char *argv[]) {
     else if (getenv("HUFF_FILES")) g_dir = getenv("HUFF_FILES");
     fprintf(stderr, "running test: %s\n", testname);
 
+    /* this harness owns the buffers it hands to the approach and releases them in evaluate_ex:
+     * let the approach page-lock them (B200_PIN=0 to measure without) */
+    b200ApproachPinBuffers(!(getenv("B200_PIN") && getenv("B200_PIN")[0] == '0'));
     struct decoder *b200 = newDecoder(b200Approach, NULL, "b200");
     /* the multi-GPU approach takes its device count the way jumptable takes jumpbits
      * (framework/mainrun.c:442,500-501); 0 = every visible device */

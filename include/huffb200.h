@@ -155,7 +155,8 @@ int  hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,
 
 /* ---- whole stream, device-resident input and output ----------------------- */
 /* d_comp: device pointer, 16-byte aligned, comp_bytes >= ceil(bits/8) readable
- * bytes.  d_out: device pointer with out_capacity bytes.  Runs on the
+ * bytes (the kernels read whole 32-bit words: comp_bytes rounded up to a multiple of 4 must
+ * be readable, which any 16-byte-granular allocation gives).  d_out: device pointer with out_capacity bytes.  Runs on the
  * context's stream, synchronises it, and fills *res. */
 int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                      uint64_t comp_bytes, uint64_t bits, void *d_out,
@@ -184,6 +185,14 @@ int hb_shard_emit(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                   uint64_t comp_bytes, uint64_t bits_own, uint64_t bits_avail,
                   const uint64_t *d_entry_base, void *d_out,
                   uint64_t out_capacity, hb_result *res);
+
+/* The same two halves with HOST buffers (one process per GPU): hb_shard_map_host uploads the
+ * shard (h_comp: comp_bytes bytes, halo included) and maps it; after the exchange and
+ * hb_shard_compose, hb_shard_emit_host emits it and downloads the bytes into h_out. */
+int hb_shard_map_host(hb_ctx *ctx, const hb_codebook *cb, const uint8_t *h_comp, uint64_t comp_bytes,
+                      uint64_t bits_own, uint64_t bits_avail, uint64_t *d_map);
+int hb_shard_emit_host(hb_ctx *ctx, const hb_codebook *cb, const uint64_t *d_entry_base,
+                       uint8_t *h_out, uint64_t out_capacity, hb_result *res);
 
 /* Result of the last hb_shard_emit on this context (synchronises its stream): for callers
  * that queued the emit with res == NULL to keep several devices busy at once. */

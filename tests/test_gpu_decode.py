@@ -95,6 +95,69 @@ def test_host_path_pipelined_chunks(dev, name, chunk):
     c.close()
 
 
+def test_host_path_pipelined_short_last_chunk_and_cut_codeword(dev):
+    """a last chunk shorter than the 16-byte halo -- the last-but-one chunk must not
+    count bits (nor read bytes) past the end of the stream.  The stream is also cut inside a
+    codeword and decoded twice into a context whose cached device buffer holds the bytes of a
+    LONGER earlier decode behind the new end: the cut-off codeword must emit nothing."""
+    f = _stream("kjv")
+    st = O.load_huff(O.corpus_path("kjv"))
+    chunk = 65536
+    c = hb.Context(0)
+    c.set_host_chunk(chunk)
+    out = np.zeros(f.usize + 16, dtype=np.uint8)
+    hb.decode_host(c, f.tree, f.data, f.bits, out[: f.usize])          # fills the cached buffers
+    for tail_bytes in (1, 7, 15):
+        for cut in (0, 3):
+            nbytes = 30 * chunk + tail_bytes
+            bits = 8 * nbytes - cut
+            want = O.simple_decode(st, bits=bits)
+            for _ in range(2):
+                out[:] = 0
+                res = hb.decode_host(c, f.tree, f.data[: nbytes + 8].copy(), bits, out[: want.size])
+                assert res["n_symbols"] == want.size, (tail_bytes, cut)
+                assert np.array_equal(out[: want.size], want), (tail_bytes, cut)
+    c.close()
+
+
+def test_shard_host_halves_match_oracle(dev):
+    """hb_shard_map_host / hb_shard_emit_host: the rank-local halves with host buffers, here for
+    two shards decoded one after the other on one GPU (the exchange done by hand)"""
+    f = _stream("kjv")
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    cb = hb.Codebook(c, f.tree)
+    nbytes = f.nbytes
+    per = (nbytes // 2) // 16 * 16
+    maps = torch.zeros(64, dtype=torch.int64, device=dev)
+    eb = torch.zeros(4, dtype=torch.int64, device=dev)
+    outs = []
+    geo = []
+    for r in range(2):
+        a = r * per
+        b = nbytes if r == 1 else per
+        halo = min(nbytes, b + 16)
+        own = f.bits - 8 * a if r == 1 else 8 * (b - a)
+        avail = own if r == 1 else min(f.bits - 8 * a, 8 * (halo - a))
+        geo.append((a, halo, own, avail))
+    # pass 1: both maps (a real run has one rank per shard; here the second map overwrites the
+    # context's state, so shard 0 is mapped again before its emit)
+    for r in (0, 1):
+        a, halo, own, avail = geo[r]
+        hb.shard_map_host(c, cb, f.data[a:halo].copy(), halo - a, own, avail, maps[32 * r:].data_ptr())
+    for r in (0, 1):
+        a, halo, own, avail = geo[r]
+        hb.shard_map_host(c, cb, f.data[a:halo].copy(), halo - a, own, avail, 0)
+        hb.shard_compose(c, maps.data_ptr(), 2, r, eb.data_ptr())
+        h_out = np.zeros(f.usize, dtype=np.uint8)
+        res = hb.shard_emit_host(c, cb, eb.data_ptr(), h_out)
+        outs.append(h_out[: res["n_symbols"]].copy())
+        assert res["out_base"] == (0 if r == 0 else outs[0].size)
+    got = np.concatenate(outs)
+    assert got.size == f.usize and O.sha256(got) == O.CORPORA["kjv"][2]
+    cb.close()
+    c.close()
+
+
 @pytest.mark.parametrize("name", ["hello", "paper1", "news", "book2", "kjv"])
 def test_approach_drop_in(name):
     """The bigtable suite (framework/mainrun.c:541-588) calling convention:

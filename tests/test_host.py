@@ -152,3 +152,19 @@ def test_models_and_generator():
         ref = np.bincount(np.fromfile(pt, dtype=np.uint8), minlength=256) / 4047392
         got = np.bincount(s, minlength=256) / s.size
         assert np.abs(ref - got).max() < 0.005
+
+
+def test_huff_header_promising_more_data_than_the_file_holds(tmp_path):
+    """an HUF8 header is untrusted -- a bit count the file cannot back (or one that
+    would wrap (bits + 7) / 8) is a format error, not a multi-exabyte allocation"""
+    import struct
+    src = O.corpus_path("hello")
+    raw = open(src, "rb").read()
+    nodes = struct.unpack(">i", raw[4:8])[0]
+    body = raw[16: 16 + 9 * nodes]
+    for bits in (2 ** 64 - 3, 2 ** 40, 8 * 5):   # hello holds 4 data bytes
+        p = tmp_path / f"bad{bits}.huff"
+        p.write_bytes(b"HUF8" + struct.pack(">i", nodes) + struct.pack(">QQ", bits, 11) + body + raw[16 + 9 * nodes:])
+        with pytest.raises(hb.HuffError) as e:
+            hb.HuffFile.load(str(p))
+        assert e.value.code == -8

@@ -1,39 +1,104 @@
-import torch, time
-n = 1 << 30
-d = torch.empty(n, dtype=torch.uint8, device="cuda")
-h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-h2 = torch.empty(n // 2, dtype=torch.uint8, pin_memory=True)
-d2 = torch.empty(n // 2, dtype=torch.uint8, device="cuda")
-s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-def t(fn, reps=5):
-    fn(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps): fn()
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / reps
-a = t(lambda: h.copy_(d, non_blocking=True))
-b = t(lambda: d.copy_(h, non_blocking=True))
-def both():
-    with torch.cuda.stream(s1): h.copy_(d, non_blocking=True)
-    with torch.cuda.stream(s2): d2.copy_(h2, non_blocking=True)
-c = t(both)
-print(f"D2H 1 GiB alone {n / a / 1e9:.1f} GB/s; H2D alone {n / b / 1e9:.1f} GB/s; D2H 1 GiB with 0.5 GiB H2D concurrently: {c * 1e3:.1f} ms = {n / c / 1e9:.1f} GB/s D2H-equivalent")
+"""Copies-only probe of the host <-> device paths the end-to-end numbers run over.
 
-# the host path's traffic pattern without any compute: 18 uploads of 32 MiB queued on one
-# stream, a 61 MB download per chunk on another as soon as "its" upload has landed
-nin, nout, K = 588_538_415, n, 18
-hin = torch.empty(nin, dtype=torch.uint8, pin_memory=True)
-din = torch.empty(nin, dtype=torch.uint8, device="cuda")
-ci, co = (nin + K - 1) // K, (nout + K - 1) // K
-def pipe():
+  python tools/pcie_probe.py                                  one GPU
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/pcie_probe.py
+                                                              N ranks, one GPU each, all at once
+
+No decode kernel runs: only the pinned-memory copies of bench.py's end-to-end legs (per rank
+588.5 MB up, 1 GiB down: one english1g shard).  With N ranks the copies of all ranks run
+simultaneously between barriers, which is what the N-GPU end-to-end leg does; the aggregate
+tells whether the host (memory, root complexes) or the decode limits that leg.
+Prints one JSON line on rank 0."""
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device(f"cuda:{local}")
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+NIN, NOUT = 588_538_415, 1 << 30
+d_out = torch.empty(NOUT, dtype=torch.uint8, device=dev)
+h_out = torch.empty(NOUT, dtype=torch.uint8, pin_memory=True)
+h_in = torch.empty(NIN, dtype=torch.uint8, pin_memory=True)
+d_in = torch.empty(NIN, dtype=torch.uint8, device=dev)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, reps=4):
+    fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    barrier()
+    dt = (time.perf_counter() - t0) / reps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def up():
+    d_in.copy_(h_in, non_blocking=True)
+
+
+def down():
+    h_out.copy_(d_out, non_blocking=True)
+
+
+def up_then_down():          # the N > 1 end-to-end leg: upload, (exchange), download
+    d_in.copy_(h_in, non_blocking=True)
+    h_out.copy_(d_out, non_blocking=True)
+
+
+def both():                  # both directions at once
+    with torch.cuda.stream(s1):
+        d_in.copy_(h_in, non_blocking=True)
+    with torch.cuda.stream(s2):
+        h_out.copy_(d_out, non_blocking=True)
+
+
+K = 18
+ci, co = (NIN + K - 1) // K, (NOUT + K - 1) // K
+
+
+def pipeline():              # hb_decode_host's pattern: chunk k's download behind chunk k's upload
     evs = []
     with torch.cuda.stream(s1):
         for k in range(K):
-            din[k * ci:(k + 1) * ci].copy_(hin[k * ci:(k + 1) * ci], non_blocking=True)
-            e = torch.cuda.Event(); e.record(s1); evs.append(e)
+            d_in[k * ci:(k + 1) * ci].copy_(h_in[k * ci:(k + 1) * ci], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s1)
+            evs.append(e)
     with torch.cuda.stream(s2):
         for k in range(K):
             s2.wait_event(evs[k])
-            h[k * co:(k + 1) * co].copy_(d[k * co:(k + 1) * co], non_blocking=True)
-p = t(pipe, 3)
-print(f"chunked pipeline pattern, copies only: {p * 1e3:.1f} ms = {nout / p / 1e9:.1f} GB/s decoded-equivalent")
+            h_out[k * co:(k + 1) * co].copy_(d_out[k * co:(k + 1) * co], non_blocking=True)
+
+
+res = {}
+for name, fn, nbytes in (("h2d", up, NIN), ("d2h", down, NOUT), ("h2d_then_d2h", up_then_down, NIN + NOUT),
+                         ("h2d_and_d2h_concurrent", both, NIN + NOUT), ("chunked_pipeline", pipeline, NIN + NOUT)):
+    dt = timed(fn)
+    res[name] = {"ms": dt * 1e3, "per_rank_GBps": nbytes / dt / 1e9, "aggregate_GBps": world * nbytes / dt / 1e9,
+                 "decoded_equiv_GBps_aggregate": world * NOUT / dt / 1e9 if "d2h" in name or "pipeline" in name else None}
+if rank == 0:
+    print(json.dumps({"probe": "pinned host<->device copies, no kernels", "ranks": world,
+                      "bytes_up_per_rank": NIN, "bytes_down_per_rank": NOUT, "results": res}), flush=True)
+if world > 1:
+    dist.destroy_process_group()
