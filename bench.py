@@ -229,6 +229,7 @@ class Job:
         self.comp[: halo_end - a] = whole[a:halo_end]
         del whole
         torch.cuda.empty_cache()
+        ctx.set_shard_origin(a)    # this rank's shard begins at byte a of the stream
         self.bits_own = self.bits_total - 8 * a if last else 8 * (b - a)
         self.bits_avail = self.bits_own if last else min(self.bits_total - 8 * a, 8 * (halo_end - a))
         self.comp_bytes_own = (self.bits_own + 7) // 8

@@ -73,7 +73,7 @@ class LutC(C.Structure):
                 ("fsm_bstep", C.POINTER(C.c_uint16)), ("fsm_depth", C.c_uint8 * 256),
                 ("fsm_pstep", C.c_uint16 * 256), ("e64", C.POINTER(C.c_uint32)),
                 ("fsm_node", C.c_int32 * 256), ("node_state", C.POINTER(C.c_int32)),
-                ("wf64", C.c_uint32), ("implied_avg_len", C.c_double)]
+                ("wf64", C.c_uint32), ("implied_avg_len", C.c_double), ("len_gcd", C.c_uint32)]
 
 
 class RefCompressedData(C.Structure):
@@ -116,6 +116,7 @@ def lib():
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_set_emit_table.argtypes = [vp, i32, i32]
+    L.hb_ctx_set_shard_origin.argtypes = [vp, u64, i32]
     L.hb_ctx_sync.argtypes = [vp]
     L.hb_ctx_set_host_chunk.argtypes = [vp, u64]
     L.hb_ctx_timing_begin.argtypes = [vp, i32]
@@ -163,6 +164,8 @@ def lib():
     L.hb_gen_verify_device.argtypes = [vp, C.POINTER(ModelC), u64, u64, u64, vp, C.POINTER(u64)]
     L.hb_gen_count_bits_device.argtypes = [vp, C.POINTER(ModelC), u64, u64, u64, C.POINTER(u64)]
     L.hb_lut_build.argtypes = [vp, i32, i32, i32, C.POINTER(LutC)]
+    L.hb_lut_sizeof.restype = C.c_size_t
+    assert L.hb_lut_sizeof() == C.sizeof(LutC), "LutC no longer mirrors struct hb_lut (csrc/hb_lut.h)"
     L.hb_lut_free.argtypes = [C.POINTER(LutC)]
     L.hb_lut_free.restype = None
     for name in ("b200Approach",):
@@ -243,7 +246,7 @@ def build_lut(tree, w1_max=0, w2_max=0):
             "wf": lut.wf,
             "stab": np.ctypeslib.as_array(lut.stab, shape=(1 << lut.wf,)).copy(),
             "etab": np.ctypeslib.as_array(lut.etab, shape=(1 << lut.wf,)).copy(),
-            "wf64": lut.wf64, "implied_avg_len": lut.implied_avg_len,
+            "wf64": lut.wf64, "implied_avg_len": lut.implied_avg_len, "len_gcd": lut.len_gcd,
             "e64": np.ctypeslib.as_array(lut.e64, shape=(2 << lut.wf64,)).copy(),
             "code": np.array(lut.code, dtype=np.uint32), "codelen": np.array(lut.codelen, dtype=np.uint8),
         }
@@ -314,6 +317,11 @@ class Context:
     def set_emit_table(self, index_bits=0, log2_copies=-1):
         """EP-table geometry of the flat emit kernel (0 / -1 = automatic)."""
         _check(lib().hb_ctx_set_emit_table(self.h, index_bits, log2_copies), "hb_ctx_set_emit_table")
+
+    def set_shard_origin(self, first_byte=None):
+        """index, in the whole stream, of the first byte of the shards decoded next (None = unknown)"""
+        _check(lib().hb_ctx_set_shard_origin(self.h, 0 if first_byte is None else first_byte,
+                                             0 if first_byte is None else 1), "hb_ctx_set_shard_origin")
 
     def set_sync_path(self, path):
         """"auto" (transducer sync kernel for streams of two waves of tiles or more), "probe"

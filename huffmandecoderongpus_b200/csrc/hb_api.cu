@@ -71,6 +71,8 @@ struct hb_ctx {
     cudaEvent_t pipe_t0 = nullptr, pipe_t1 = nullptr;
     uint64_t *h_res = nullptr; /* pinned, 8 words */
     uint64_t hs_readable = 0, hs_own = 0, hs_avail = 0;   /* shard of the last hb_shard_map_host */
+    bool origin_known = false;    /* hb_ctx_set_shard_origin */
+    uint64_t origin_byte = 0;
 };
 
 static const char *const k_errs[] = {
@@ -216,6 +218,13 @@ extern "C" int hb_ctx_set_emit_table(hb_ctx *ctx, int index_bits, int log2_copie
     if (log2_copies < -1 || log2_copies > 4) return HB_ERR_ARG;
     ctx->ep_wf = index_bits;
     ctx->ep_rshift = log2_copies;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_set_shard_origin(hb_ctx *ctx, uint64_t first_byte, int known) {
+    if (!ctx) return HB_ERR_ARG;
+    ctx->origin_known = known != 0;
+    ctx->origin_byte = known ? first_byte : 0;
     return HB_OK;
 }
 
@@ -427,6 +436,15 @@ static int make_args(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp, uin
     a->minlen = cb->lut.minlen;
     a->fast = cb->d_lut + cb->lut.n_entries;   /* S-table; the E-table follows it */
     a->wf = cb->lut.wf;
+    /* entry offsets that cannot occur are not followed (hb_stream_args.gmod) */
+    if (ctx->origin_known) {
+        a->gmod = cb->lut.len_gcd ? cb->lut.len_gcd : 1u;
+        a->gorg = (uint32_t)((ctx->origin_byte % a->gmod) * 8u % a->gmod);
+    } else {
+        a->gmod = 1u;
+        while (a->gmod < 32u && cb->lut.len_gcd % (2u * a->gmod) == 0u) a->gmod *= 2u;
+        a->gorg = 0u;
+    }
     return HB_OK;
 }
 
@@ -860,10 +878,17 @@ extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *
     if (!res) res = &local;
     if (!ctx) return HB_ERR_ARG;
     ctx->fuse_small = true;    /* nobody reads the shard map between the two phases */
+    const bool ok0 = ctx->origin_known;
+    const uint64_t ob0 = ctx->origin_byte;
+    ctx->origin_known = true;  /* a whole stream: its first byte is byte 0 */
+    ctx->origin_byte = 0;
     int rc = hb_shard_map(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr);
     ctx->fuse_small = false;
-    if (rc) return rc;
-    return hb_shard_emit(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr, d_out, out_capacity, res);
+    if (rc == HB_OK)
+        rc = hb_shard_emit(ctx, cb, d_comp, comp_bytes, bits, bits, nullptr, d_out, out_capacity, res);
+    ctx->origin_known = ok0;
+    ctx->origin_byte = ob0;
+    return rc;
 }
 
 /* Large host-resident streams: the compressed bytes are cut into chunks (byte-range
@@ -877,7 +902,11 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
 
 static int decode_host_pipelined(hb_ctx *ctx, hb_codebook *cb, const uint8_t *data, uint64_t bits,
                                  uint8_t *out, uint64_t out_capacity, hb_result *res) {
+    const bool ok0 = ctx->origin_known;
+    const uint64_t ob0 = ctx->origin_byte;
     int rc = decode_host_pipelined_run(ctx, cb, data, bits, out, out_capacity, res);
+    ctx->origin_known = ok0;
+    ctx->origin_byte = ob0;
     if (rc != HB_OK) {
         /* copies may still be in flight to/from the caller's buffers: drain them
          * before the error is reported */
@@ -948,6 +977,8 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
         const uint64_t readable = last || a + cbytes + 16 > padded + 32 ? padded + 32 - a : cbytes + 16;
         uint64_t *h = ctx->h_pipe + 36 * (size_t)k;
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * k], 0));
+        ctx->origin_known = true;    /* chunk k begins at byte a of the stream */
+        ctx->origin_byte = a;
         if ((rc = hb_shard_map(ctx, cb, d_comp + a, readable, own, avail, nullptr))) return rc;
         CK(cudaMemcpyAsync(h, ctx->misc.p, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

@@ -138,11 +138,7 @@ HB_HD uint32_t hb_ctz(uint32_t v) {   /* v != 0 */
 }
 
 HB_HD uint32_t hb_acc_add(uint32_t acc, uint32_t ent) {   /* acc += ent >> 16 */
-#if defined(__CUDA_ARCH__) && defined(HB_USE_DP2A)
-    return __dp2a_lo(ent, 0x0100u, acc);
-#else
     return acc + (ent >> 16);
-#endif
 }
 
 /* ent >> 16, written so that the compiler does not fold it with the in-loop

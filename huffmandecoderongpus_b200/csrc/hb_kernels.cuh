@@ -46,6 +46,15 @@ struct hb_stream_args {
     uint32_t minlen;         /* == maxlen: fixed-length code, closed-form chains */
     const uint32_t *fast;    /* S-table (sync kernel) or E-table (emit kernel), 1 << wf entries */
     uint32_t wf;
+    uint32_t gmod, gorg;     /* When every codeword length is a multiple of g, codeword starts stay in ONE
+                              * residue class mod g of the stream's bit positions (the stream begins on a
+                              * codeword).  A tile at bit position P of the stream can then only be entered
+                              * at offsets e with (P + e) % g == 0; chains of other offsets never merge with
+                              * the true one -- following them anyway (round 1) made such codes 18 to 100
+                              * times slower.  gmod = g when the shard's position in the stream is known
+                              * (hb_ctx_set_shard_origin; gorg = that position in bits mod g), else the
+                              * largest power of two dividing g, which needs no position because shards,
+                              * chunks and tiles all begin at multiples of 128 bits (gorg = 0). */
 };
 
 /* fast-table footprint in shared memory, kept a multiple of 16 bytes */
@@ -59,6 +68,14 @@ __host__ __device__ __forceinline__ uint32_t hb_lut_smem_words(uint32_t wf) {
 __device__ __forceinline__ uint32_t hb_opaque(uint32_t v) {
     asm volatile("" : "+r"(v));
     return v;
+}
+
+/* may a chain enter tile `tile` (tile_bits bits per tile) at offset e?  (hb_stream_args.gmod) */
+__device__ __forceinline__ bool hb_entry_possible(const hb_stream_args &a, uint32_t tile, uint32_t tile_bits,
+                                                  uint32_t e) {
+    if (a.gmod <= 1u) return true;
+    const uint32_t p = (a.gorg + (tile % a.gmod) * (tile_bits % a.gmod) + e) % a.gmod;
+    return p == 0u;
 }
 
 /* device status word bits */
@@ -206,7 +223,7 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
             const uint32_t wl = (tile_lim - 1u) >> 5;           /* last owned word */
             const uint32_t X0 = hb_rec_land(s_rec[(wl % WPT) * T + wl / WPT]);
             uint32_t m = hb_map_pack32(X0, C0);
-            if (t > 0 && (uint32_t)t < a.maxlen) {
+            if (t > 0 && (uint32_t)t < a.maxlen && hb_entry_possible(a, tile, TS, (uint32_t)t)) {
                 if (fixed_len) {   /* never merges: arithmetic progression t, t+len, ... */
                     const uint32_t n = hb_fixed_count((uint32_t)t, a.maxlen, 0u, tile_lim);
                     m = hb_map_pack32((hb_fixed_next((uint32_t)t, a.maxlen, tile_lim) - tile_lim) & 31u, n);
@@ -464,7 +481,7 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
         if (t < 32) {
             const uint32_t X0 = s_warp[12], d0 = s_warp[13];
             uint32_t m = hb_map_pack32(X0, E0 + (d0 ? 1u : 0u));
-            if (t > 0 && t < a.maxlen) {
+            if (t > 0 && t < a.maxlen && hb_entry_possible(a, tile, (uint32_t)(T * 32 * WPT), t)) {
                 hb_global_words word{a.words, (uint64_t)tile * (T * WPT), a.nwords};
                 m = hb_fsm_hyp_walk<WPT, T>(f, slow, word, s_rec, s_cs, E0, X0, d0, t);
             }

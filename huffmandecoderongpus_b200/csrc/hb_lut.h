@@ -6,6 +6,7 @@
 #ifndef HB_LUT_H_
 #define HB_LUT_H_
 
+#include <stddef.h>
 #include <stdint.h>
 #include "huffb200.h"
 
@@ -45,6 +46,7 @@ typedef struct hb_lut {
     int32_t  *node_state;
     uint32_t  wf64;              /* index width of the E64-table (hb_format.h) */
     double    implied_avg_len;   /* sum over leaves of 2^-len * len */
+    uint32_t  len_gcd;           /* gcd of all codeword lengths (1 for almost every real code) */
 } hb_lut;
 
 /* Validate the tree and build the table.  w1_max/w2_max cap the widths of the
@@ -56,6 +58,7 @@ int hb_lut_build(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut 
  * (hb_build_tables_kernel), the host only validates and numbers the states. */
 int hb_lut_build_small(const hb_node *tree, int nodes, int w1_max, int w2_max, hb_lut *out);
 void hb_lut_free(hb_lut *lut);
+size_t hb_lut_sizeof(void);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 
 extern "C" int hb_gen_ctx_stream(hb_ctx *ctx, int *device, void **stream);
 
@@ -42,8 +47,27 @@ struct hb_mdev {
     uint64_t n_symbols = 0, out_base = 0;
 };
 
+/* One host thread per device: the ~25 CUDA runtime calls a decode queues on a device take
+ * ~60 us of host time, which, issued from a single thread for 8 devices one after the other,
+ * was most of the wall time of a 1 GiB-symbol decode on 8 GPUs (0.55 ms against 0.25 ms with
+ * one process per GPU).  The workers are parked on a condition variable between calls. */
+struct hb_pool {
+    std::thread th[HB_MULTI_MAX];
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(int)> job;
+    uint64_t job_seq = 0;
+    int n = 0, pending = 0;
+    int rc[HB_MULTI_MAX];
+    bool quit = false;
+};
+
 struct hb_multi {
     int n = 0;
+    hb_pool *pool = nullptr;
+    std::atomic<uint64_t> map_issued[HB_MULTI_MAX];   /* run number whose ev_map record has been queued */
+    std::atomic<int> abort_run{0};
+    uint64_t run_no = 0;
     hb_mdev d[HB_MULTI_MAX];
     hb_node_abi *tree = nullptr;
     int nodes = 0;
@@ -78,11 +102,64 @@ static double now_ms(void) {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+static void pool_worker(hb_pool *p, int i, int device) {
+    cudaSetDevice(device);
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<int(int)> job;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_job.wait(lk, [&] { return p->quit || p->job_seq != seen; });
+            if (p->quit) return;
+            seen = p->job_seq;
+            job = p->job;
+        }
+        const int rc = job(i);
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->rc[i] = rc;
+            if (--p->pending == 0) p->cv_done.notify_all();
+        }
+    }
+}
+
+/* run fn(i) for every device i < n on its own thread; first non-zero result */
+static int pool_run(hb_multi *m, int n, const std::function<int(int)> &fn) {
+    hb_pool *p = m->pool;
+    if (!p || n <= 1) {
+        int rc = HB_OK;
+        for (int i = 0; i < n && rc == HB_OK; i++) rc = fn(i);
+        return rc;
+    }
+    {
+        std::unique_lock<std::mutex> lk(p->mu);
+        p->job = [fn, n](int i) { return i < n ? fn(i) : HB_OK; };
+        p->pending = p->n;
+        p->job_seq++;
+    }
+    p->cv_job.notify_all();
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->cv_done.wait(lk, [&] { return p->pending == 0; });
+    for (int i = 0; i < n; i++)
+        if (p->rc[i] != HB_OK) return p->rc[i];
+    return HB_OK;
+}
+
 extern "C" const char *hb_multi_last_error(const hb_multi *m) { return m ? m->err : "no multi context"; }
 extern "C" int hb_multi_devices(const hb_multi *m) { return m ? m->n : 0; }
 
 extern "C" void hb_multi_destroy(hb_multi *m) {
     if (!m) return;
+    if (m->pool) {
+        {
+            std::lock_guard<std::mutex> lk(m->pool->mu);
+            m->pool->quit = true;
+        }
+        m->pool->cv_job.notify_all();
+        for (int i = 0; i < m->pool->n; i++) m->pool->th[i].join();
+        delete m->pool;
+        m->pool = nullptr;
+    }
     for (int i = 0; i < m->n; i++) {
         hb_mdev &v = m->d[i];
         cudaSetDevice(v.device);
@@ -143,6 +220,14 @@ extern "C" int hb_multi_create(const int *devices, int n_devices, hb_multi **out
         }
     }
     cudaGetLastError();
+    for (int i = 0; i < HB_MULTI_MAX; i++) m->map_issued[i].store(0);
+    if (m->n > 1 && !(getenv("HB_MULTI_THREADS") && getenv("HB_MULTI_THREADS")[0] == '0')) {
+        m->pool = new (std::nothrow) hb_pool();
+        if (m->pool) {
+            m->pool->n = m->n;
+            for (int i = 0; i < m->n; i++) m->pool->th[i] = std::thread(pool_worker, m->pool, i, m->d[i].device);
+        }
+    }
     *out = m;
     return HB_OK;
 }
@@ -206,37 +291,74 @@ static void cut_shards(hb_multi *m, uint64_t bits) {
     }
 }
 
-/* map on every device, maps of the left neighbours copied over, compose: all asynchronous */
-static int queue_maps(hb_multi *m) {
-    for (int i = 0; i < m->n_active; i++) {
-        hb_mdev &v = m->d[i];
-        MCK(cudaSetDevice(v.device));
-        MCK(cudaEventRecord(v.ev_start, v.stream));
-        MRC(hb_shard_map(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_maps + 32 * i));
-        MCK(cudaEventRecord(v.ev_map, v.stream));
+/* Per device (on its own host thread): map, then the maps of the left neighbours are copied
+ * over and composed; optionally the emit right behind.  All asynchronous on the device's
+ * stream.  A cross-device cudaStreamWaitEvent only orders against an event record that has
+ * already been QUEUED, so device i first waits (on the host) until its left neighbours have
+ * queued theirs for this run. */
+static int dev_fail(hb_multi *m, int i, int rc, const char *what) {
+    snprintf(m->err, sizeof(m->err), "device %d: %s: %s (%s)", m->d[i].device, what, hb_strerror(rc),
+             hb_last_error(m->d[i].ctx));
+    m->abort_run.store(1);
+    return rc;
+}
+static int dev_cuda(hb_multi *m, int i, cudaError_t e, const char *what) {
+    snprintf(m->err, sizeof(m->err), "device %d: %s: %s", m->d[i].device, what, cudaGetErrorString(e));
+    m->abort_run.store(1);
+    return HB_ERR_CUDA;
+}
+#define DCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return dev_cuda(m, i, e_, #call); } while (0)
+
+static int dev_map(hb_multi *m, int i, uint64_t run, bool upload, const uint8_t *data) {
+    hb_mdev &v = m->d[i];
+    int rc;
+    cudaError_t e = cudaSetDevice(v.device);
+    if (e == cudaSuccess && upload) {
+        if (v.bytes) e = cudaMemcpyAsync(v.d_comp, data + v.a, v.bytes, cudaMemcpyHostToDevice, v.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(v.d_comp + v.bytes, 0, v.readable - v.bytes, v.stream);
     }
-    for (int i = 0; i < m->n_active; i++) {
-        hb_mdev &v = m->d[i];
-        MCK(cudaSetDevice(v.device));
-        for (int r = 0; r < i; r++) {
-            MCK(cudaStreamWaitEvent(v.stream, m->d[r].ev_map, 0));
-            MCK(cudaMemcpyPeerAsync(v.d_maps + 32 * r, v.device, m->d[r].d_maps + 32 * r, m->d[r].device,
-                                    32 * sizeof(uint64_t), v.stream));
-        }
-        MRC(hb_shard_compose(v.ctx, v.d_maps, i + 1, i, v.d_eb));
+    if (e == cudaSuccess) e = cudaEventRecord(v.ev_start, v.stream);
+    rc = e == cudaSuccess ? hb_ctx_set_shard_origin(v.ctx, v.a, 1) : HB_ERR_CUDA;
+    if (rc == HB_OK)
+        rc = hb_shard_map(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_maps + 32 * i);
+    if (rc == HB_OK && (e = cudaEventRecord(v.ev_map, v.stream)) != cudaSuccess) rc = HB_ERR_CUDA;
+    if (rc != HB_OK) m->abort_run.store(1);
+    m->map_issued[i].store(run, std::memory_order_release);   /* even on failure: nobody may wait for ever */
+    if (e != cudaSuccess) return dev_cuda(m, i, e, "map phase");
+    if (rc != HB_OK) return dev_fail(m, i, rc, "hb_shard_map");
+    for (int r = 0; r < i; r++) {
+        while (m->map_issued[r].load(std::memory_order_acquire) != run) std::this_thread::yield();
+        if (m->abort_run.load()) return HB_ERR_STATE;
+        DCK(cudaStreamWaitEvent(v.stream, m->d[r].ev_map, 0));
+        DCK(cudaMemcpyPeerAsync(v.d_maps + 32 * r, v.device, m->d[r].d_maps + 32 * r, m->d[r].device,
+                                32 * sizeof(uint64_t), v.stream));
     }
+    if ((rc = hb_shard_compose(v.ctx, v.d_maps, i + 1, i, v.d_eb))) return dev_fail(m, i, rc, "hb_shard_compose");
     return HB_OK;
 }
 
-static int queue_emits(hb_multi *m) {
-    for (int i = 0; i < m->n_active; i++) {
-        hb_mdev &v = m->d[i];
-        MCK(cudaSetDevice(v.device));
-        MRC(hb_shard_emit(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_eb, v.d_out,
-                          v.out_cap, nullptr));
-        MCK(cudaEventRecord(v.ev_end, v.stream));
-    }
+static int dev_emit(hb_multi *m, int i) {
+    hb_mdev &v = m->d[i];
+    DCK(cudaSetDevice(v.device));
+    int rc = hb_shard_emit(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_eb, v.d_out,
+                           v.out_cap, nullptr);
+    if (rc) return dev_fail(m, i, rc, "hb_shard_emit");
+    DCK(cudaEventRecord(v.ev_end, v.stream));
     return HB_OK;
+}
+
+static int queue_maps(hb_multi *m, bool upload = false, const uint8_t *data = nullptr, bool emit_too = false) {
+    const uint64_t run = ++m->run_no;
+    m->abort_run.store(0);
+    return pool_run(m, m->n_active, [m, run, upload, data, emit_too](int i) {
+        int rc = dev_map(m, i, run, upload, data);
+        if (rc == HB_OK && emit_too) rc = dev_emit(m, i);
+        return rc;
+    });
+}
+
+static int queue_emits(hb_multi *m) {
+    return pool_run(m, m->n_active, [m](int i) { return dev_emit(m, i); });
 }
 
 /* entry/base/total of every shard back to the host (one small copy per device) */
@@ -374,8 +496,7 @@ extern "C" int hb_multi_generate(hb_multi *m, int model_kind, uint64_t seed, uin
 extern "C" int hb_multi_decode(hb_multi *m, hb_multi_result *res) {
     if (!m || !m->loaded) return HB_ERR_STATE;
     const double t0 = now_ms();
-    int rc = queue_maps(m);
-    if (rc == HB_OK) rc = queue_emits(m);
+    int rc = queue_maps(m, false, nullptr, true);
     if (rc != HB_OK) return rc;
     for (int i = 0; i < m->n_active; i++) {
         MCK(cudaSetDevice(m->d[i].device));
@@ -434,11 +555,8 @@ extern "C" int hb_multi_decode_host(hb_multi *m, const hb_node_abi *tree, int no
     for (int i = 0; i < m->n_active; i++) {
         hb_mdev &v = m->d[i];
         if ((rc = grow(m, v, &v.d_comp, &v.comp_cap, (size_t)v.readable))) return rc;
-        MCK(cudaSetDevice(v.device));
-        if (v.bytes) MCK(cudaMemcpyAsync(v.d_comp, data + v.a, v.bytes, cudaMemcpyHostToDevice, v.stream));
-        MCK(cudaMemsetAsync(v.d_comp + v.bytes, 0, v.readable - v.bytes, v.stream));
     }
-    if ((rc = queue_maps(m))) return rc;
+    if ((rc = queue_maps(m, true, data))) return rc;
     if ((rc = fetch_bases(m))) return rc;
     if (m->n_symbols > out_capacity + 1) {   /* + 1: a cut-off last codeword is counted until the emit */
         snprintf(m->err, sizeof(m->err), "decoded size %llu exceeds the output buffer (%llu)",

@@ -120,6 +120,13 @@ int  hb_ctx_sync(hb_ctx *ctx);
  * compressed bytes (rounded to whole tiles) and overlaps upload, decode and
  * download; 0 restores the default (32 MiB). */
 int  hb_ctx_set_host_chunk(hb_ctx *ctx, uint64_t bytes);
+/* Where the next shards begin in their stream: first_byte = index, in the WHOLE stream, of the
+ * first byte handed to hb_shard_map (known = 0: unknown, the default).  Optional, and only a
+ * speed matter: for codes whose codeword lengths all share a factor g that is not a power of
+ * two, it lets the kernels skip entry offsets that cannot occur at that position (their chains
+ * never merge with the true one and are slow to follow).  hb_decode_device, hb_decode_host and
+ * hb_multi_* set it themselves. */
+int  hb_ctx_set_shard_origin(hb_ctx *ctx, uint64_t first_byte, int known);
 /* Phase timing over many steps without host synchronisation in between:
  * _begin arms a ring of max_steps CUDA-event sets (one per following
  * hb_shard_map + hb_shard_emit pair); _collect synchronises the stream and

@@ -43,7 +43,10 @@ struct Emul {
     static constexpr uint32_t TS = T * S;
 
     const uint32_t *words; uint64_t nwords, bits_own, bits_avail; uint32_t ntiles;
-    hb_tables tbS, tbE; uint32_t maxlen, minlen;
+    hb_tables tbS, tbE; uint32_t maxlen, minlen, gmod = 1, gorg = 0;   /* see hb_stream_args */
+    bool possible(uint32_t tile, uint32_t e) const {
+        return gmod <= 1u || (gorg + (tile % gmod) * (TS % gmod) + e) % gmod == 0u;
+    }
     hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) */
     bool flat = false;                       /* flat walk (EP-table) on all tiles but the last */
     std::vector<uint32_t> eptab; uint32_t ep_wf = 10;   /* plain EP-table */
@@ -150,7 +153,7 @@ struct Emul {
         const uint32_t X0 = hb_rec_land(s_rec[(wl % WPT) * T + wl / WPT]);
         for (uint32_t t = 0; t < 32; t++) {
             uint32_t m = hb_map_pack32(X0, C0);
-            if (t > 0 && t < maxlen) {
+            if (t > 0 && t < maxlen && possible(tile, t)) {
                 if (minlen == maxlen) {
                     const uint32_t n = hb_fixed_count(t, maxlen, 0u, tile_lim);
                     m = hb_map_pack32((hb_fixed_next(t, maxlen, tile_lim) - tile_lim) & 31u, n);
@@ -215,7 +218,7 @@ struct Emul {
         auto word = [&](uint32_t i) -> uint32_t { return tbase + i < nwords ? words[tbase + i] : 0u; };
         for (uint32_t t = 0; t < 32; t++) {
             uint32_t m = hb_map_pack32(X0, E0 + (d0 ? 1u : 0u));
-            if (t > 0 && t < maxlen) {
+            if (t > 0 && t < maxlen && possible(tile, t)) {
                 m = hb_fsm_hyp_walk<WPT, T>(fsm, tbS.slow, word, s_rec.data(), s_cs.data(), E0, X0, d0, t);
                 if ((m & 31u) != X0) st.hyp_unmerged++;
             }
@@ -473,8 +476,11 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
                int have_entry, uint32_t entry, uint64_t base, uint8_t *out, uint64_t out_capacity,
                uint64_t *shard_map, uint64_t *result, emul_stats *stats, uint32_t emit_win,
                int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab, const uint8_t *fsm_depth,
-               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, uint32_t wf64, uint32_t ep_wf) {
+               const uint16_t *fsm_pstep, int emit_mode, const uint32_t *e64, uint32_t wf64, uint32_t ep_wf,
+               uint32_t gmod, uint32_t gorg) {
     Emul<WPT, T> E;
+    E.gmod = gmod ? gmod : 1u;
+    E.gorg = gorg;
     E.emit_mode = emit_mode == 2 ? 1 : emit_mode;
     E.flat = emit_mode == 2 && WPT >= 4;
     E.sync_mode = sync_mode;
@@ -534,13 +540,13 @@ extern "C" int emul_run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxle
                         uint64_t *result, emul_stats *stats, uint32_t emit_win,
                         int sync_mode, uint32_t fsm_states, const uint16_t *fsm_tab,
                         const uint8_t *fsm_depth, const uint16_t *fsm_pstep, int emit_mode,
-                        const uint32_t *e64, uint32_t wf64, uint32_t ep_wf) {
+                        const uint32_t *e64, uint32_t wf64, uint32_t ep_wf, uint32_t gmod, uint32_t gorg) {
 #define CASE(W, TT)                                                                              \
     if (wpt == W && T == TT)                                                                     \
         return run<W, TT>(lut_entries, w1, maxlen, minlen, stab, etab, wf, words, nwords,        \
                           bits_own, bits_avail, have_entry, entry, base, out, out_capacity,      \
                           shard_map, result, stats, emit_win, sync_mode, fsm_states, fsm_tab,    \
-                          fsm_depth, fsm_pstep, emit_mode, e64, wf64, ep_wf)
+                          fsm_depth, fsm_pstep, emit_mode, e64, wf64, ep_wf, gmod, gorg)
     CASE(4, 256); CASE(8, 256); CASE(16, 256);
     CASE(1, 4); CASE(2, 8); CASE(4, 32); CASE(1, 64);
 #undef CASE

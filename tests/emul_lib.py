@@ -43,9 +43,21 @@ def lib():
                                C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                C.c_void_p, C.POINTER(Stats), C.c_uint32,
                                C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
+                               C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
+
+
+def gmod_of(lut, origin_byte=0):
+    """(gmod, gorg) as make_args in csrc/hb_api.cu computes them; origin_byte = None: the shard's
+    position in the stream is unknown -> only the power-of-two part of the gcd is usable"""
+    g = int(lut["len_gcd"]) or 1
+    if origin_byte is None:
+        h = 1
+        while h < 32 and g % (2 * h) == 0:
+            h *= 2
+        return h, 0
+    return g, (origin_byte % g) * 8 % g
 
 
 def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
@@ -57,7 +69,7 @@ def words_of(data: np.ndarray, nbytes: int) -> np.ndarray:
 
 
 def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=True,
-        out_capacity=None, out_offset=0, emit_win=0, sync_mode=2, emit_mode=1, ep_wf=10):
+        out_capacity=None, out_offset=0, emit_win=0, sync_mode=2, emit_mode=1, ep_wf=10, origin_byte=0):
     """Returns (out bytes, shard_map[32], result[4], stats dict, rc).
     sync_mode: 0 = probe sync kernel only, 1 = transducer kernel on full tiles (the
     product's default dispatch), 2 = both, failing (rc -101) unless they agree.
@@ -83,7 +95,7 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
                         words.size, bits_own, bits_avail, wpt, T, int(emit), entry, base,
                         out.ctypes.data, cap, smap.ctypes.data, res.ctypes.data, C.byref(st), emit_win,
                         sync_mode, lut["fsm_states"], fsm.ctypes.data, fdepth.ctypes.data,
-                        fpstep.ctypes.data, emit_mode, e64.ctypes.data, lut["wf64"], ep_wf)
+                        fpstep.ctypes.data, emit_mode, e64.ctypes.data, lut["wf64"], ep_wf, *gmod_of(lut, origin_byte))
     return out, smap, res, st.as_dict(), rc
 
 

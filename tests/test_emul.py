@@ -455,3 +455,54 @@ def test_flat_emit_random_codes(seed):
         assert rc == 0 and int(res[0]) == n, tag
         assert np.array_equal(out[:n], want), tag
         assert not out[n:].any(), tag
+
+
+# ---- codes whose lengths share a factor: entry offsets off the residue class never occur ----
+
+@pytest.mark.parametrize("lengths", [
+    [2, 2, 2, 4, 4, 4, 4],                       # all even (the documented 18x cliff of round 1)
+    [2] * 3 + [4] * 3 + [6] * 3 + [8] * 3 + [10] * 3 + [12] * 3 + [14] * 3 + [16] * 4,   # even, long tail
+    [4] * 15 + [8] * 16,                         # multiples of 4
+    [8] * 255 + [16] * 256,                      # multiples of 8, more than 256 internal nodes
+    [3, 3, 3, 3, 3, 3, 3, 6, 6, 6, 6, 6, 6, 6, 6],   # multiples of 3: no power of two, full path
+    [6] * 63 + [12] * 64,                        # gcd 6 -> only the factor 2 is used
+])
+@pytest.mark.parametrize("shape", [(8, 256), (4, 32), (1, 4)])
+def test_codes_with_a_common_length_factor(lengths, shape):
+    tree, codes = O.tree_from_lengths(lengths)
+    lut = hb.build_lut(tree)
+    g = 0
+    for l in lengths:
+        g = np.gcd(g, l)
+    assert lut["len_gcd"] == g
+    rng = np.random.default_rng(sum(lengths))
+    n = 60000 if shape[1] == 256 else 4000
+    syms = rng.integers(0, len(lengths), n)
+    data, bits = O.encode_with_codes(codes, syms)
+    st = O.Stream(tree, data, bits, n)
+    want = (syms & 255).astype(np.uint8)
+    for mode in (1, 2):
+        got, stats, rc = E.decode(st, *shape, lut=lut, emit_mode=mode)
+        assert rc == 0 and np.array_equal(got, want), (mode,)
+    # byte-range shards of the same stream (shards start at multiples of 128 bits)
+    w = E.words_of(st.data, st.nbytes)
+    nb = (bits + 7) // 8
+    cut = (nb // 2) // 16 * 16
+    if cut >= 16 and shape[1] == 256:
+        outs = []
+        entry, base = 0, 0
+        for (a, b) in ((0, cut), (cut, nb)):
+            last = b == nb
+            own = bits - 8 * a if last else 8 * (b - a)
+            avail = own if last else min(bits - 8 * a, 8 * (b + 16 - a))
+            for origin in (a, None):    # the shard's position in the stream known / unknown
+                out, smap, res, _, rc = E.run(lut, w[a // 4:], own, avail, *shape, entry=entry, base=base,
+                                              origin_byte=origin)
+                assert rc == 0
+                assert np.array_equal(out[: int(res[0])], want[base: base + int(res[0])])
+            outs.append(out[: int(res[0])].copy())
+            m = int(smap[entry])
+            entry, base = m & 31, base + (m >> 8)
+            if not last:
+                assert (8 * b + entry) % g == 0     # codeword starts stay in one residue class
+        assert np.array_equal(np.concatenate(outs), want)
