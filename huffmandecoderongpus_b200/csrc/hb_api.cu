@@ -703,12 +703,31 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     if (ctx->emit_path != HB_EMIT_BYTES) {
         ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
         ae.wf = cb->lut.wf64;                     /* ... and its own index width */
-        smem += (size_t)8 << ae.wf;               /* the table sits in front of the staging buffer */
-        if ((rc = grid_for(ctx, hb_emitw_kernel<WPT>, smem, a.ntiles - tile0, &grid))) return rc;
-        hb_emitw_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
-            ae, tile0, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-            (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win,
-            (uint32_t *)(misc + 36));
+        /* G groups of 256 threads share R = G copies of the table: the same shared memory per
+         * thread as one copy per 256 threads, fewer bank conflicts (hb_tables64).  Streams of
+         * at least two tiles per SM; hb_ctx_set_emit_table's log2_copies overrides (0 / 1 / 2). */
+        uint32_t rs = 0;
+        const uint32_t left = a.ntiles - tile0;
+        if (ctx->ep_rshift >= 0) rs = ctx->ep_rshift > 2 ? 2u : (uint32_t)ctx->ep_rshift;
+        else if (left >= 4u * (uint32_t)ctx->prop.multiProcessorCount) rs = 2u;   /* measured: english1g emit 0.775 -> 0.747 ms, fib4g 1.85 -> 1.75 (2 copies: no change) */
+        const uint32_t grp = sizeof(uint32_t) * hb_emitw_group_words(stage);
+        /* fewer copies when table + groups would not fit an SM (large staging windows) */
+        while (rs > 0 && ((size_t)8 << (ae.wf + rs)) + ((size_t)grp << rs) > (size_t)ctx->prop.sharedMemPerBlockOptin) rs--;
+        const uint32_t G = 1u << rs;
+        smem = ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp;   /* the table sits in front of the groups */
+        const uint32_t need = (left + G - 1u) / G;
+#define HB_LAUNCH_EMITW(GG)                                                                              \
+        do {                                                                                             \
+            if ((rc = grid_for(ctx, hb_emitw_kernel<WPT, GG>, smem, need, &grid, GG * HB_T))) return rc;   \
+            hb_emitw_kernel<WPT, GG><<<grid, GG * HB_T, smem, ctx->stream>>>(                             \
+                ae, tile0, rs, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,         \
+                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, win, stage,               \
+                (uint32_t *)(misc + 36));                                                                \
+        } while (0)
+        if (G == 4) HB_LAUNCH_EMITW(4);
+        else if (G == 2) HB_LAUNCH_EMITW(2);
+        else HB_LAUNCH_EMITW(1);
+#undef HB_LAUNCH_EMITW
     } else {
         ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
         if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;

@@ -374,10 +374,14 @@ HB_HD uint32_t hb_emit_slow(const hb_lutref &lut, const uint32_t (&w)[WPT + 1], 
  * Probes read the E64-table (hb_format.h): LDS.64, up to three symbols.  A 32-bit
  * variant with two symbols per probe was measured slower (0.98 vs 0.78 ms) and dropped. */
 struct hb_tables64 {
-    const uint32_t *fast;  /* E64-table (host emulation) */
+    const uint32_t *fast;  /* E64-table (host emulation: plain, sc = 3, laneoff = 0) */
     uint32_t fast_saddr;   /* its shared-state-space address (device) */
-    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << 3 */
+    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << sc */
     hb_lutref slow;
+    /* device: the table may be held in R = 1 << (sc - 3) copies interleaved entry by entry
+     * (copy r of entry x at byte (x << sc) + 8 r); a lane reads copy laneoff / 8, so that
+     * lanes of different copies never share a bank and fewer LDS.64 wavefronts are replays */
+    uint32_t sc = 3u, laneoff = 0u;
 };
 
 /* one probe: symbols (first in the low byte), sel (low 16 bits: PRMT selector for the
@@ -401,12 +405,12 @@ HB_HD uint32_t hb_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, uint32_t acc) {
-    const uint32_t x = hb_funnel_r(los, his, acc) & tb.fmask;
+    const uint32_t x = (hb_funnel_r(los, his, acc) & tb.fmask) | tb.laneoff;
     uint32_t lo, hi;
 #ifdef __CUDA_ARCH__
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(x + tb.fast_saddr));
 #else
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + x);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tb.fast) + (x >> (tb.sc - 3u)));
     lo = q[0];
     hi = q[1];
 #endif
@@ -467,7 +471,7 @@ struct hb_tail { hb_out_t at; uint32_t k, bytes; };   /* k bytes (low first) to 
 template <int WPT>
 HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
                             uint32_t c, hb_out_t out, uint32_t mis) {
-    constexpr uint32_t SC = 3u;                       /* window pre-scale: log2(bytes per entry) */
+    const uint32_t SC = tb.sc;                        /* window pre-scale: log2(bytes per entry and copy set) */
     uint32_t acc = e, pend = 0u, posk = 8u * mis;     /* acc: bit position in the current word */
     hb_out_t wpp = out - mis;                         /* next staging word to store */
 #pragma unroll
@@ -534,7 +538,7 @@ HB_HD hb_tail hb_emit_words(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1],
 template <int WPT>
 HB_HD uint32_t hb_emit_clipped(const hb_tables64 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
                                uint32_t e, uint32_t c, hb_out_t out) {
-    constexpr uint32_t SC = 3u;
+    const uint32_t SC = tb.sc;
     uint32_t acc = e, n = 0u;
 #pragma unroll
     for (int j = 0; j < WPT; j++) {

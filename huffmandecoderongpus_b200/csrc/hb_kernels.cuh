@@ -815,27 +815,43 @@ hb_fix_fixed_kernel(hb_stream_args a, const uint8_t *__restrict__ tile_entry,
 #ifndef HB_EMITW_MIN_CTAS
 #define HB_EMITW_MIN_CTAS 4
 #endif
-template <int WPT>
-__global__ void __launch_bounds__(HB_T, HB_EMITW_MIN_CTAS)
-hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ subs,
+/* per-group shared memory in 32-bit words (16-byte multiple) */
+__host__ __device__ __forceinline__ uint32_t hb_emitw_group_words(uint32_t stage_bytes) {
+    return 16u + stage_bytes / 4u;
+}
+
+/* A CTA is G groups of HB_T threads, each on its own tile behind its own named barrier,
+ * sharing ONE copy set of the E64-table (R = 1 << rshift copies, hb_tables64): with G = 2 and
+ * R = 2 the table costs the same shared memory per thread as one copy per 256 threads, and
+ * lanes 0-7 / 8-15 of each half-warp read different copies (different banks). */
+template <int WPT, int G>
+__global__ void __launch_bounds__(G * HB_T, HB_EMITW_MIN_CTAS / G)
+hb_emitw_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, const uint16_t *__restrict__ subs,
                const uint64_t *__restrict__ tile_base, const uint64_t *__restrict__ result, uint8_t *__restrict__ out,
-               uint64_t out_capacity, uint32_t win, uint32_t *__restrict__ status) {
+               uint64_t out_capacity, uint32_t win, uint32_t stage_bytes, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
     constexpr uint32_t TS = T * S;
     constexpr uint32_t EW = 2u;                            /* words per E64 entry */
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_fast = smem;                               /* E64-table: 2 << a.wf words (a.wf = its own width) */
-    uint32_t *s_warp = smem + (EW << a.wf);                /* 16 */
+    const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
+    uint32_t *s_fast = smem;                               /* E64-table: (2 << a.wf) << rshift words */
+    uint32_t *s_warp = smem + ((EW << a.wf) << rshift) + g * hb_emitw_group_words(stage_bytes);   /* 16 */
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
-    const int t = threadIdx.x;
 
-    for (uint32_t i = t; i < (EW << a.wf); i += T) s_fast[i] = __ldg(a.fast + i);
+    {
+        const uint2 *src = reinterpret_cast<const uint2 *>(a.fast);
+        uint2 *dst = reinterpret_cast<uint2 *>(s_fast);
+        for (uint32_t i = threadIdx.x; i < ((1u << a.wf) << rshift); i += G * T) dst[i] = __ldg(src + (i >> rshift));
+    }
     __syncthreads();
     hb_tables64 tb64;
     tb64.fast = s_fast;
     tb64.fast_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_fast));
-    tb64.fmask = ((1u << a.wf) - 1u) << 3;
+    tb64.sc = 3u + rshift;
+    tb64.fmask = ((1u << a.wf) - 1u) << tb64.sc;
+    /* a half-warp (one LDS.64 wavefront group) spreads over all copies */
+    tb64.laneoff = hb_opaque(((t >> (4u - rshift)) & ((1u << rshift) - 1u)) << 3);   /* rshift <= 4 */
     tb64.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
@@ -843,7 +859,8 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ s
     /* software pipeline: the next tile's words, record and output base are fetched as
      * soon as this tile's words are dead (after its last decode window), so that the
      * loads fly during the copy-out, the barriers and the next scan */
-    uint32_t tile = tile0 + blockIdx.x, nwin = 0;
+    const uint32_t tstep = gridDim.x * G;
+    uint32_t tile = tile0 + blockIdx.x * G + g, nwin = 0;
     uint32_t w[WPT + 1];
     uint16_t sub = 0;
     uint64_t B = 0;
@@ -855,12 +872,12 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ s
     while (tile < a.ntiles) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
         const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
-        const uint32_t next = tile + gridDim.x;
+        const uint32_t next = tile + tstep;
         const uint64_t Bt = B;
 
         const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
         uint32_t nk;
-        const uint32_t o = hb_block_exscan(c, s_warp, &nk);
+        const uint32_t o = hb_group_exscan(c, s_warp, bar, t, &nk);
         const uint32_t lim = sub0 >= a.bits_own ? 0u
                            : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
         /* symbols past the shard's valid total (a cut-off last codeword) are not written */
@@ -887,7 +904,7 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ s
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 *s_hi = nk;                                  /* default: last window */
             }
-            __syncthreads();
+            hb_group_sync(bar);
             hb_tail tl;
             tl.k = 0u;
             if (mine) {
@@ -901,14 +918,14 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ s
                 sub = subs[(uint64_t)next * T + t];
                 B = tile_base[next];
             }
-            __syncthreads();
+            hb_group_sync(bar);
             /* every word store is done: the last, partial word of each slice (its other
              * lanes belong to the right neighbour, who has just overwritten them) */
             hb_store_tail(tl);
             /* every thread orders its own staging writes before the async proxy (the bulk
              * store below reads them), then the barrier orders the threads */
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
+            hb_group_sync(bar);
             uint32_t hi_b = *s_hi;
             if (hi_b > nvalid) hi_b = nvalid;
             if (lo_b < hi_b) {
@@ -941,6 +958,7 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, const uint16_t *__restrict__ s
             hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
             sub = subs[(uint64_t)next * T + t];
             B = tile_base[next];
+            hb_group_sync(bar);      /* the scan of the next tile reuses s_warp */
         }
         tile = next;
     }

@@ -491,7 +491,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     hb_lutref slow{lut_entries, lut_entries, (1u << w1) - 1u};
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
-    E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow};
+    E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow, 3u, 0u};
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);
