@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ep-wf", type=int, default=0, help="EP-table index bits of the flat emit kernel (0 = auto)")
     ap.add_argument("--ep-copies-log2", type=int, default=-1, help="log2 of the EP-table copies (-1 = auto)")
-    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat"],
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat", "words32"],
                     help="emit kernel A/B (auto = words)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe", "fsm"],
                     help="sync kernel A/B")
@@ -392,7 +392,7 @@ def main():
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
     sync_name = "hb_sync_kernel" if args.sync_path == "probe" else "hb_fsm_sync_kernel"
-    emit_name = {"bytes": "hb_emit_kernel", "flat": "hb_emitf_kernel"}.get(args.emit_path, "hb_emitw_kernel")
+    emit_name = {"bytes": "hb_emit_kernel", "flat": "hb_emitf_kernel", "words": "hb_emitw_kernel"}.get(args.emit_path, "hb_emit32_kernel")
     dom_name = {"sync": sync_name, "emit": emit_name}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this

@@ -36,7 +36,8 @@ struct hb_ctx {
     int ctas_per_sm = 0;
     int sync_path = HB_SYNC_AUTO;
     int emit_path = HB_EMIT_AUTO;
-    int ep_wf = 0, ep_rshift = -1;   /* EP-table geometry of the flat emit kernel (0 / -1 = automatic) */
+    int ep_wf = 0, ep_rshift = -1;   /* EP-/E32-table geometry of the flat / 32-bit emit kernels (0 / -1 = automatic) */
+    uint32_t smem_base = 0x400;      /* shared-window address at which a kernel's dynamic shared memory begins (measured) */
     int phase_timing = HB_PHASES_AUTO;
     bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
     bool map_fused = false;       /* the last hb_shard_map left up/top to hb_scan_small_kernel */
@@ -116,6 +117,11 @@ static int ensure(hb_ctx *ctx, hb_buf &b, size_t bytes) {
     return HB_OK;
 }
 
+__global__ void hb_smem_base_kernel(uint32_t *out) {
+    extern __shared__ __align__(16) uint32_t smem_probe[];
+    if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(smem_probe);
+}
+
 extern "C" int hb_ctx_create(int device, void *cuda_stream, hb_ctx **out) {
     if (!out) return HB_ERR_ARG;
     *out = nullptr;
@@ -152,6 +158,20 @@ extern "C" int hb_ctx_create(int device, void *cuda_stream, hb_ctx **out) {
         if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return HB_ERR_CUDA;
+    }
+    /* where dynamic shared memory begins in the shared window: hb_emit32_kernel places its table at
+     * a multiple of the table size (it verifies the address itself and reports HB_ST_LAYOUT) */
+    {
+        uint32_t *d_base = nullptr;
+        if (cudaMalloc((void **)&d_base, sizeof(uint32_t)) == cudaSuccess) {
+            hb_smem_base_kernel<<<1, 32, 16, ctx->stream>>>(d_base);
+            uint32_t b = 0;
+            if (cudaMemcpyAsync(&b, d_base, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+                ctx->smem_base = b & 0xffffffu;    /* the bits above are the CTA's rank in its cluster */
+            cudaFree(d_base);
+        }
+        cudaGetLastError();
     }
     *out = ctx;
     return HB_OK;
@@ -206,7 +226,8 @@ extern "C" int hb_ctx_set_phase_timing(hb_ctx *ctx, int mode) {
 }
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
-    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS && path != HB_EMIT_FLAT))
+    if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS && path != HB_EMIT_FLAT &&
+                 path != HB_EMIT_WORDS32))
         return HB_ERR_ARG;
     ctx->emit_path = path;
     return HB_OK;
@@ -214,7 +235,7 @@ extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
 
 extern "C" int hb_ctx_set_emit_table(hb_ctx *ctx, int index_bits, int log2_copies) {
     if (!ctx) return HB_ERR_ARG;
-    if (index_bits != 0 && (index_bits < HB_EP_WF_MIN || index_bits > HB_EP_WF_MAX)) return HB_ERR_ARG;
+    if (index_bits != 0 && (index_bits < HB_EP_WF_MIN || index_bits > HB_E32_WF_MAX)) return HB_ERR_ARG;
     if (log2_copies < -1 || log2_copies > 4) return HB_ERR_ARG;
     ctx->ep_wf = index_bits;
     ctx->ep_rshift = log2_copies;
@@ -608,6 +629,7 @@ static int launch_emit_flat(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_
     *launched = false;
     hb_stream_args ae = a;
     uint32_t wf = ctx->ep_wf ? (uint32_t)ctx->ep_wf : 10u;
+    if (wf > HB_EP_WF_MAX) wf = HB_EP_WF_MAX;
     if (wf > cb->lut.maxlen && cb->lut.maxlen >= HB_EP_WF_MIN) wf = cb->lut.maxlen;   /* no longer codeword exists */
     uint32_t rshift = ctx->ep_rshift >= 0 ? (uint32_t)ctx->ep_rshift : 4u;
     const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
@@ -700,7 +722,45 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     }
     /* staging stores: whole words, three symbols per probe (english1g 0.75 ms vs 0.81 with
      * byte stores); the byte-store kernel on request */
-    if (ctx->emit_path != HB_EMIT_BYTES) {
+    /* 32-bit table entries, three symbols per probe, 4 (or 8) copies on disjoint banks, the table
+     * at a multiple of its size (hb_emit32_kernel): streams of at least four tiles per SM */
+    bool done32 = false;
+    if (WPT >= 2 && (ctx->emit_path == HB_EMIT_WORDS32 ||
+                     (ctx->emit_path == HB_EMIT_AUTO && cb->lut.wf64 == HB_WF_MAX &&   /* short codes: four symbols per probe pay (fib4g 1.75 vs 1.85 ms) */
+                      a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount))) {
+        constexpr uint32_t G = 4;
+        /* index width: 14 bits (2.65 symbols per probe on English text against 2.3 with 12, a tenth of
+         * the long-codeword fallbacks) where the 16 K-entry table is worth building: every CTA builds
+         * its own copy, ~10 us, so only from 16 tiles per SM on */
+        uint32_t wf32 = a.ntiles - tile0 >= 16u * (uint32_t)ctx->prop.multiProcessorCount ? 14u : 12u;
+        if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
+        if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;   /* no longer codeword exists */
+        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : (wf32 >= 14u ? 0u : (wf32 == 13u ? 1u : 2u));
+        const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
+        const size_t grp = sizeof(uint32_t) * (size_t)hb_emitw_group_words(stage);
+        for (;; rs--) {
+            const size_t tab = (size_t)4 << (wf32 + rs);
+            const size_t abs0 = ((size_t)ctx->smem_base + tab - 1) / tab * tab;
+            const size_t tab_off = abs0 - ctx->smem_base;
+            size_t n_before = tab_off / grp;
+            if (n_before > G) n_before = G;
+            const size_t total = tab_off + tab + (G - n_before) * grp;
+            if (total <= limit) {
+                ae.wf = wf32;
+                const uint32_t need = (a.ntiles - tile0 + G - 1u) / G;
+                if ((rc = grid_for(ctx, hb_emit32_kernel<WPT, G>, total, need, &grid, G * HB_T))) return rc;
+                hb_emit32_kernel<WPT, G><<<grid, G * HB_T, total, ctx->stream>>>(
+                    ae, tile0, rs, (uint32_t)tab_off, (uint32_t)n_before, (const uint16_t *)ctx->subs.p,
+                    (const uint64_t *)ctx->tile_base.p, (const uint64_t *)(misc + 32), (uint8_t *)d_out,
+                    out_capacity, win, stage, (uint32_t *)(misc + 36));
+                done32 = true;
+                break;
+            }
+            if (rs == 0) break;
+        }
+    }
+    if (done32) {
+    } else if (ctx->emit_path != HB_EMIT_BYTES) {
         ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
         ae.wf = cb->lut.wf64;                     /* ... and its own index width */
         /* G groups of 256 threads share R = G copies of the table: the same shared memory per
@@ -816,6 +876,10 @@ static int finish_result(hb_ctx *ctx, uint32_t ntiles, uint32_t launches, hb_res
     }
     if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]) == cudaSuccess) res->ms_total = ms;
     cudaGetLastError();
+    if ((uint32_t)ctx->h_res[4] & HB_ST_LAYOUT) {
+        snprintf(ctx->err, sizeof(ctx->err), "hb_emit32_kernel: table not aligned to its size (dynamic shared memory base moved)");
+        return HB_ERR_CUDA;
+    }
     if ((uint32_t)ctx->h_res[4] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
     return HB_OK;
 }
@@ -1031,6 +1095,7 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
     if (cudaEventElapsedTime(&ms, ctx->pipe_t0, ctx->pipe_t1) == cudaSuccess) res->ms_total = ms;
     /* output-full raised inside a kernel */
     CK(cudaMemcpy(ctx->h_res, misc_words(ctx) + 36, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if ((uint32_t)ctx->h_res[0] & HB_ST_LAYOUT) return HB_ERR_CUDA;
     if ((uint32_t)ctx->h_res[0] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
     return HB_OK;
 }

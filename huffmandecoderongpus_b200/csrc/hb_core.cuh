@@ -575,6 +575,187 @@ HB_HD void hb_store_tail(const hb_tail &tl) {
         if (i < tl.k) hb_st8(tl.at, i, tl.bytes >> (8u * i));
 }
 
+/* ==== emit walk with word-granular stores, 32-bit table entries (hb_emit32_kernel) ==========
+ * Same staging discipline as hb_emit_words (register window, whole-word stores, tail after the
+ * barrier), but the probes read the E32-table: ONE 32-bit word per index,
+ *     [23:0]  first .. third symbol, one byte each (at most HB_E32_MAXSYM)
+ *     [25:24] nsym, [31:26] bits consumed; marker (not even one codeword fits): nsym = 0,
+ *             bits = HB_E64_MARK
+ * An LDS.32 of a warp is one wavefront group of 32 lanes (an LDS.64 is two of 16), and a table of
+ * half the size leaves room for twice the copies: measured 2.1 wavefronts per probe against 4.8.
+ * No ready-made selector is needed: "shift nsym new bytes into the window" is a funnel shift by
+ * 8 * nsym, and the table's top byte, which rides along in the symbol word, is shifted out of
+ * every staging word that is stored (a word completes only when at least one byte was pending,
+ * because a probe brings at most three).
+ * The loops are plain do-while loops with a single exit (one probe per trip): the divergent
+ * exits of the two-probe form made every group of lanes run the long-codeword test on its own. */
+#define HB_E32_MAXSYM 3
+struct hb_tables32 {
+    const uint32_t *fast;  /* E32-table (host emulation: plain, sc = 2, lanebase = 0) */
+    uint32_t fmask;        /* byte-offset mask: ((1 << wf) - 1) << sc */
+    uint32_t lanebase;     /* device: shared address of the table (aligned to its size, so that it can be
+                            * OR-ed in) | byte offset of this lane's copy; copies are interleaved entry by
+                            * entry (copy r of entry x at byte (x << sc) + 4 r) and sit on disjoint banks */
+    hb_lutref slow;
+    uint32_t sc, wf;
+};
+
+/* E32 entry of index x (wf bits, LSB first) from the single-symbol table */
+HB_HD uint32_t hb_e32_entry(const hb_lutref &slow, uint32_t x, uint32_t wf) {
+    uint32_t pos = 0, n = 0, syms = 0;
+    while (n < HB_E32_MAXSYM && pos < wf) {
+        uint32_t sym;
+        const uint32_t len = hb_probe(slow, x >> pos, 0u, 0u, &sym);
+        if (pos + len > wf) break;           /* would use bits beyond the index */
+        syms |= sym << (8u * n);
+        n++;
+        pos += len;
+    }
+    return n ? (syms | (n << 24) | (pos << 26)) : (HB_E64_MARK << 26);
+}
+
+HB_HD uint32_t hb_probe32(const hb_tables32 &tb, uint32_t los, uint32_t his, uint32_t acc) {
+    const uint32_t x = (hb_funnel_r(los, his, acc) & tb.fmask) | tb.lanebase;
+#ifdef __CUDA_ARCH__
+    uint32_t ent;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(x));
+    return ent;
+#else
+    return tb.fast[x >> tb.sc];
+#endif
+}
+
+/* entry standing for one codeword decoded by the single-symbol table */
+HB_HD uint32_t hb_e32_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, uint32_t pos) {
+    uint32_t sym;
+    const uint32_t len = hb_probe(slow, lo, hi, pos, &sym);
+    return sym | (1u << 24) | (len << 26);
+}
+
+HB_HD uint32_t hb_e32_nsym(uint32_t ent) { return (ent >> 24) & 3u; }
+HB_HD uint32_t hb_e32_shift(uint32_t ent) { return (ent >> 21) & 0x18u; }   /* 8 * nsym */
+
+/* shift the first t / 8 symbols of ent into the window; store the staging word they complete */
+HB_HD uint32_t hb_push32(uint32_t ent, uint32_t t, uint32_t &pend, uint32_t posk, hb_out_t &wpp) {
+    const uint32_t word = hb_funnel_l(pend, ent, posk);      /* pending bytes below the new ones */
+    const uint32_t posk_n = posk + t;
+    pend = hb_funnel_r(pend, ent, t);
+    if ((posk ^ posk_n) & 0x20u) { hb_st32(wpp, 0u, word); wpp += 4; }
+    return posk_n;
+}
+
+template <int WPT>
+HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
+                              uint32_t c, hb_out_t out, uint32_t mis) {
+    const uint32_t SC = tb.sc;
+    uint32_t acc = e, pend = 0u, posk = 8u * mis;
+    hb_out_t wpp = out - mis;
+#pragma unroll
+    for (int j = 0; j < WPT - 1; j++) {
+        const uint32_t lo = w[j], hi = w[j + 1];
+        const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
+        for (;;) {
+            do {
+                const uint32_t ent = hb_probe32(tb, los, his, acc);
+                posk = hb_push32(ent, hb_e32_shift(ent), pend, posk, wpp);
+                acc += ent >> 26;
+            } while (!(acc & 0xE0u));
+            if (acc < HB_E64_MARK) break;
+            /* the last entry was the marker: a codeword longer than the index starts there */
+            acc -= HB_E64_MARK;
+            const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
+            posk = hb_push32(ent, 8u, pend, posk, wpp);
+            acc += ent >> 26;
+            if (acc & 0xE0u) break;
+        }
+        acc -= 32u;
+    }
+    {   /* last word.  Probes that start at or below bit 32 - wf end inside the word: all their
+         * symbols are this chain's.  Only the one or two probes after that can run into the next
+         * subsequence; their symbols are clipped to the chain's count c. */
+        const uint32_t lo = w[WPT - 1], hi = w[WPT];
+        const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
+        const uint32_t safe = 32u - tb.wf;
+        bool done = false;
+        for (;;) {
+            if (acc <= safe) {
+                do {
+                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    posk = hb_push32(ent, hb_e32_shift(ent), pend, posk, wpp);
+                    acc += ent >> 26;
+                } while (acc <= safe);
+            }
+            if (acc < HB_E64_MARK) break;
+            acc -= HB_E64_MARK;              /* a long codeword that starts at or below `safe`: ours */
+            const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
+            posk = hb_push32(ent, 8u, pend, posk, wpp);
+            acc += ent >> 26;
+            if (acc & 0xE0u) { done = true; break; }
+        }
+        if (!done) {
+            uint32_t n = (uint32_t)(wpp - out) + ((posk >> 3) & 3u);   /* symbols pushed so far */
+            for (;;) {
+                while (!(acc & 0xE0u)) {
+                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    const uint32_t ns = hb_e32_nsym(ent);
+                    uint32_t t = 8u * ns;
+                    if (n + ns > c) t = n < c ? 8u * (c - n) : 0u;
+                    posk = hb_push32(ent, t, pend, posk, wpp);
+                    n += ns;
+                    acc += ent >> 26;
+                }
+                if (acc < HB_E64_MARK) break;
+                acc -= HB_E64_MARK;
+                const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
+                posk = hb_push32(ent, n < c ? 8u : 0u, pend, posk, wpp);
+                n += 1u;
+                acc += ent >> 26;
+                if (acc & 0xE0u) break;      /* a long codeword may end past HB_E64_MARK: not a marker */
+            }
+        }
+    }
+    hb_tail tl;
+    tl.k = (posk >> 3) & 3u;
+    tl.bytes = tl.k ? pend >> ((32u - 8u * tl.k) & 31u) : 0u;
+    tl.at = wpp;
+    return tl;
+}
+
+/* Partial subsequence (stream tail): byte stores, every symbol clipped to the chain's count c */
+template <int WPT>
+HB_HD uint32_t hb_emit_clipped32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
+                                 uint32_t e, uint32_t c, hb_out_t out) {
+    const uint32_t SC = tb.sc;
+    uint32_t acc = e, n = 0u;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        if (32u * j < lim) {
+            const uint32_t lo = w[j], hi = w[j + 1];
+            const uint32_t los = lo << SC, his = hb_funnel_l(lo, hi, SC);
+            for (;;) {
+                while (!(acc & 0xE0u)) {
+                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    const uint32_t ns = hb_e32_nsym(ent);
+#pragma unroll
+                    for (uint32_t i = 0; i < HB_E32_MAXSYM; i++)
+                        if (i < ns && n + i < c) hb_st8(out, n + i, ent >> (8u * i));
+                    n += ns;
+                    acc += ent >> 26;
+                }
+                if (acc < HB_E64_MARK) break;
+                acc -= HB_E64_MARK;
+                const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
+                if (n < c) hb_st8(out, n, ent);
+                n += 1u;
+                acc += ent >> 26;
+                if (acc & 0xE0u) break;
+            }
+            acc -= 32u;
+        }
+    }
+    return n < c ? n : c;
+}
+
 /* ==== flat emit walk (hb_emitf_kernel) =========================================
  * One loop over the whole chain of a subsequence instead of one loop per stream word: the
  * words come from shared memory (a column per thread, so the reads are conflict free) into

@@ -44,6 +44,7 @@
 #define HB_EP_MARK 0x80000000u
 #define HB_EP_WF_MIN 8
 #define HB_EP_WF_MAX 12
+#define HB_E32_WF_MAX 15          /* widest E32-table index (hb_emit32_kernel): 128 KB for one copy */
 
 /* Byte-step transducer of the sync kernel's fast path (the GPU counterpart of the
  * reference's jump table, framework/jumptableapproach.c:40-99, with jumpbits = 8 and

@@ -967,6 +967,146 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, const uint16_
 }
 
 /* ------------------------------------------------------------------------- */
+/* Emit kernel with 32-bit table entries (hb_emit_words32 in hb_core.cuh): the default for large
+ * streams.  Same tile pipeline as hb_emitw_kernel; the differences are the table and the probe
+ * loops.
+ *   - The E32-table is built by the CTA itself from the single-symbol table (one thread per index,
+ *     R = 1 << rshift copies interleaved entry by entry: copy r on banks r, r + R, ...; lane l reads
+ *     copy l & (R - 1), so that only the 32 / R lanes of one copy can collide).
+ *   - The table sits at a shared-memory address that is a multiple of its size (tab_off, computed
+ *     by the host from the dynamic window's base address), so that "base | index | copy" is ONE
+ *     LOP3 and the probe's address needs no add.  The groups' staging buffers fill the room in
+ *     front of the table first (n_before of them), the rest follow it. */
+#define HB_ST_LAYOUT 2u       /* the E32-table is not aligned to its size: host / device layout mismatch */
+template <int WPT, int G>
+__global__ void __launch_bounds__(G * HB_T, HB_EMITW_MIN_CTAS / G)
+hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab_off, uint32_t n_before,
+                 const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
+                 const uint64_t *__restrict__ result, uint8_t *__restrict__ out, uint64_t out_capacity,
+                 uint32_t win, uint32_t stage_bytes, uint32_t *__restrict__ status) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t TS = T * S;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
+    const uint32_t tab_bytes = 4u << (a.wf + rshift);
+    const uint32_t grp = hb_emitw_group_words(stage_bytes);
+    uint32_t *s_fast = smem + tab_off / 4u;
+    uint32_t *s_warp = smem + (g < n_before ? g * grp : (tab_off + tab_bytes) / 4u + (g - n_before) * grp);   /* 16 */
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
+    const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    if (tab_saddr & (tab_bytes - 1u)) {
+        if (threadIdx.x == 0) atomicOr(status, HB_ST_LAYOUT);
+        return;
+    }
+    const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
+    for (uint32_t x = threadIdx.x; x < (1u << a.wf); x += G * T) {
+        const uint32_t ent = hb_e32_entry(slow, x, a.wf);
+        for (uint32_t r = 0; r < (1u << rshift); r++) s_fast[(x << rshift) + r] = ent;
+    }
+    __syncthreads();
+    hb_tables32 tb;
+    tb.fast = s_fast;
+    tb.sc = 2u + rshift;
+    tb.wf = a.wf;
+    tb.fmask = ((1u << a.wf) - 1u) << tb.sc;
+    tb.lanebase = hb_opaque(tab_saddr | ((t & ((1u << rshift) - 1u)) << 2));
+    tb.slow = slow;
+    const uint64_t total_valid = result[0];
+    const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
+
+    const uint32_t tstep = gridDim.x * G;
+    uint32_t tile = tile0 + blockIdx.x * G + g, nwin = 0;
+    uint32_t w[WPT + 1];
+    uint16_t sub = 0;
+    uint64_t B = 0;
+    if (tile < a.ntiles) {
+        hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+        sub = subs[(uint64_t)tile * T + t];
+        B = tile_base[tile];
+    }
+    while (tile < a.ntiles) {
+        const uint64_t tile_bit0 = (uint64_t)tile * TS;
+        const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+        const uint32_t next = tile + tstep;
+        const uint64_t Bt = B;
+
+        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        uint32_t nk;
+        const uint32_t o = hb_group_exscan(c, s_warp, bar, t, &nk);
+        const uint32_t lim = sub0 >= a.bits_own ? 0u
+                           : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+        uint32_t nvalid = nk;
+        if (Bt >= total_valid) nvalid = 0;
+        else if (Bt + nk > total_valid) nvalid = (uint32_t)(total_valid - Bt);
+        const bool full_out = Bt + nvalid > out_capacity;
+        if (full_out && t == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
+
+        /* windows: see hb_emitw_kernel */
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; !full_out && (wb == 0 || wb < nk); wb += win, nwin++) {
+            const bool mine = c && o >= wb && o - wb < win;
+            const bool last_win = wb + win >= nk;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + Bt + wb) & 15u);
+            uint32_t *s_hi = s_warp + 14 + (nwin & 1u);
+            if (t == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                *s_hi = nk;
+            }
+            hb_group_sync(bar);
+            hb_tail tl;
+            tl.k = 0u;
+            if (mine) {
+                const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
+                if (lim != S) hb_emit_clipped32<WPT>(tb, w, lim, e, c, dst);
+                else tl = hb_emit_words32<WPT>(tb, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                if (o + c - wb >= win && o + c < nk) *s_hi = o + c;
+            }
+            if (last_win && next < a.ntiles) {
+                hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
+                sub = subs[(uint64_t)next * T + t];
+                B = tile_base[next];
+            }
+            hb_group_sync(bar);
+            hb_store_tail(tl);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            hb_group_sync(bar);
+            uint32_t hi_b = *s_hi;
+            if (hi_b > nvalid) hi_b = nvalid;
+            if (lo_b < hi_b) {
+                uint8_t *gbase = out + Bt + wb - al;          /* 16-byte aligned */
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
+                if (a0 < a1) {
+                    if (t == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(gbase + a0), "r"(s_out_saddr + a0), "r"(a1 - a0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (t >= 32 && t < 64) {
+                        const uint32_t i = t - 32;
+                        if (begb + i < a0) gbase[begb + i] = s_out[begb + i];
+                        if (a1 + i < endb) gbase[a1 + i] = s_out[a1 + i];
+                    }
+                } else {
+                    for (uint32_t i = begb + t; i < endb; i += T) gbase[i] = s_out[i];
+                }
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+        }
+        if (full_out && next < a.ntiles) {
+            hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
+            sub = subs[(uint64_t)next * T + t];
+            B = tile_base[next];
+            hb_group_sync(bar);
+        }
+        tile = next;
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------------- */
 /* Emit kernel, flat variant (hb_emit_flat in hb_core.cuh): full tiles that are not the last
  * tile of the shard.  A CTA is G groups of HB_T threads, each on its own tile behind its own
  * named barrier, sharing ONE EP-table built in shared memory by the CTA itself (R copies,

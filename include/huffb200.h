@@ -104,6 +104,8 @@ int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
 #define HB_EMIT_FLAT  3   /* hb_emitf_kernel (one loop per subsequence, lane-private table copies) on
                              every tile but the last; 8 words per thread only.  Experimental: measured
                              slower than HB_EMIT_WORDS, never chosen by HB_EMIT_AUTO */
+#define HB_EMIT_WORDS32 4 /* hb_emit32_kernel: word stores, 32-bit table entries with up to three symbols, 4
+                             (or 8) copies of the table on disjoint banks */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
 /* EP-table of the flat emit kernel: index width in bits (8..12, 0 = automatic) and log2 of the
  * number of copies interleaved in shared memory (0..4, -1 = automatic).  A/B knob. */

@@ -47,7 +47,8 @@ struct Emul {
     bool possible(uint32_t tile, uint32_t e) const {
         return gmod <= 1u || (gorg + (tile % gmod) * (TS % gmod) + e) % gmod == 0u;
     }
-    hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table) */
+    hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table), 3 word stores (E32-table) */
+    hb_tables32 tbE32; std::vector<uint32_t> e32tab;
     bool flat = false;                       /* flat walk (EP-table) on all tiles but the last */
     std::vector<uint32_t> eptab; uint32_t ep_wf = 10;   /* plain EP-table */
     uint64_t flat_tiles = 0;
@@ -433,10 +434,12 @@ struct Emul {
                 const uint32_t mis = (al + (o - wb)) & 3u;
                 uint32_t n = c;
                 if (lim != S && (emit_mode == 0 || WPT < 2)) n = hb_emit_slow<WPT>(tbE.slow, w, lim, e, c, dst);
-                else if (lim != S) n = hb_emit_clipped<WPT>(tbE64, w, lim, e, c, dst);
+                else if (lim != S) n = emit_mode == 3 ? hb_emit_clipped32<WPT>(tbE32, w, lim, e, c, dst)
+                                                      : hb_emit_clipped<WPT>(tbE64, w, lim, e, c, dst);
                 else if (emit_mode == 0 || WPT < 2) n = hb_emit_fast<WPT>(tbE, w, e, c, dst);
                 else if constexpr (WPT >= 2) {
-                    tails.push_back(hb_emit_words<WPT>(tbE64, w, e, c, dst, mis));
+                    tails.push_back(emit_mode == 3 ? hb_emit_words32<WPT>(tbE32, w, e, c, dst, mis)
+                                                   : hb_emit_words<WPT>(tbE64, w, e, c, dst, mis));
                     /* whole words inside the slice plus the tail make exactly c bytes */
                     if ((uint32_t)((tails.back().at + tails.back().k) - dst) != c) return false;
                 }
@@ -492,6 +495,13 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow, 3u, 0u};
+    if (emit_mode == 3) {   /* E32-table exactly as hb_emit32_kernel builds it (index width: ep_wf, else wf64) */
+        uint32_t wf32 = ep_wf ? ep_wf : wf64;
+        if (wf32 > maxlen && maxlen >= 9u) wf32 = maxlen;
+        E.e32tab.resize((size_t)1 << wf32);
+        for (uint32_t x = 0; x < (1u << wf32); x++) E.e32tab[x] = hb_e32_entry(slow, x, wf32);
+        E.tbE32 = hb_tables32{E.e32tab.data(), ((1u << wf32) - 1u) << 2, 0u, slow, 2u, wf32};
+    }
     E.maxlen = maxlen; E.minlen = minlen;
     const uint64_t tile_bits = (uint64_t)E.TS;
     E.ntiles = (uint32_t)((bits_own + tile_bits - 1) / tile_bits);

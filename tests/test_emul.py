@@ -281,17 +281,17 @@ def test_badly_synchronising_codes(lengths, shape):
     assert rc == 0 and np.array_equal(got, syms)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 @pytest.mark.parametrize("shape", [(4, 256), (8, 256), (16, 256), (2, 8)])
 @pytest.mark.parametrize("name", ["book2", "world192"])
 def test_emit_paths(name, mode, shape):
-    """byte-store emit walk (E-table) and word-store walk (E64-table) give the same bytes,
-    at every output alignment"""
+    """byte-store emit walk (E-table) and the word-store walks (E64-table, E32-table) give the
+    same bytes, at every output alignment"""
     st = _stream(name)
     lut = hb.build_lut(st.tree)
     w = E.words_of(st.data, st.nbytes)
     for off in (0, 1, 2, 3):
-        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_mode=mode, out_offset=off)
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_mode=mode, out_offset=off, ep_wf=0)
         assert rc == 0 and int(res[0]) == st.usize
         assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
         assert not out[st.usize:].any()
@@ -385,12 +385,50 @@ def test_random_codes_and_streams(seed):
         shape = [(4, 256), (8, 256), (16, 256), (2, 8), (1, 4)][int(rng.integers(5))]
         lut = hb.build_lut(tree)
         wds = E.words_of(st.data, (bits + 7) // 8)
-        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=int(rng.integers(2)),
-                                   out_offset=int(rng.integers(16)))
+        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=int(rng.choice([0, 1, 3, 3])),
+                                   ep_wf=int(rng.choice([0, 9, 10, 12, 13, 14])), out_offset=int(rng.integers(16)))
         tag = (seed, case, nleaves, maxlen, n, shape)
         assert rc == 0 and int(res[0]) == n, tag
         assert np.array_equal(out[:n], want), tag
         assert not out[n:].any(), tag
+
+
+# ---- word-store walk with 32-bit table entries (hb_emit_words32 / hb_emit32_kernel) ------
+
+@pytest.mark.parametrize("ep_wf", [0, 9, 11, 14])
+@pytest.mark.parametrize("shape", [(8, 256), (4, 32), (16, 256), (2, 8)])
+@pytest.mark.parametrize("name", ["paper1", "world192", "ecoli", "kjv"])
+def test_e32_emit_corpora(name, shape, ep_wf):
+    """E32-table probes (three symbols, funnel-shift window update), unclipped / clipped phases
+    of the last word, markers (index narrower than the longest codeword), every alignment"""
+    st = _stream(name)
+    if name == "kjv" and (shape != (8, 256) or ep_wf != 0):
+        pytest.skip("large corpus: product shape only")
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    for off in ((0, 1, 2, 3, 7, 13) if name == "paper1" else (0, 5)):
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, *shape, emit_mode=3, ep_wf=ep_wf, out_offset=off)
+        assert rc == 0 and int(res[0]) == st.usize
+        assert O.sha256(out[: st.usize]) == O.CORPORA[name][2]
+        assert not out[st.usize:].any()
+
+
+def test_e32_emit_truncated_and_windows():
+    """stream tails (partial subsequences: hb_emit_clipped32), cut-off last codewords and tiles
+    emitted in several staging windows"""
+    st = _stream("paper1")
+    lut = hb.build_lut(st.tree)
+    w = E.words_of(st.data, st.nbytes)
+    full = O.simple_decode(st)
+    for bits in (st.bits - 1, st.bits - 7, st.bits // 2 + 3, 8 * 4096 + 5, 777):
+        sub = O.Stream(st.tree, st.data, bits, 0)
+        want = O.simple_decode(sub)
+        out, _, res, _, rc = E.run(lut, w, bits, bits, 8, 256, emit_mode=3, ep_wf=0)
+        assert rc == 0 and int(res[0]) == want.size
+        assert np.array_equal(out[: want.size], want) and np.array_equal(want, full[: want.size])
+    for win in (2048, 1008, 144):
+        out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, 8, 256, emit_win=win, out_offset=3, emit_mode=3, ep_wf=0)
+        assert rc == 0 and int(res[0]) == st.usize and np.array_equal(out[: st.usize], full)
 
 
 # ---- flat emit walk (hb_emit_flat / hb_emitf_kernel) -----------------------------------
@@ -481,7 +519,7 @@ def test_codes_with_a_common_length_factor(lengths, shape):
     data, bits = O.encode_with_codes(codes, syms)
     st = O.Stream(tree, data, bits, n)
     want = (syms & 255).astype(np.uint8)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         got, stats, rc = E.decode(st, *shape, lut=lut, emit_mode=mode)
         assert rc == 0 and np.array_equal(got, want), (mode,)
     # byte-range shards of the same stream (shards start at multiples of 128 bits)

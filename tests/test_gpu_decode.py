@@ -392,9 +392,12 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto", "flat"):
+    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
-        c.set_emit_path(path)
+        if ":" in path:     # E32-table geometry: index bits, log2(copies)
+            _, wf, rs = path.split(":")
+            c.set_emit_table(int(wf), int(rs))
+        c.set_emit_path(path.split(":")[0])
         cb = hb.Codebook(c, f.tree)
         for off in (0, 1, 2, 3, 7):
             got, res, raw = _decode_dev(c, cb, f, dev, out_offset=off)
