@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--ep-copies-log2", type=int, default=-1, help="log2 of the EP-table copies (-1 = auto)")
     ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat", "words32"],
                     help="emit kernel A/B (auto = words)")
+    ap.add_argument("--sync-copies-log2", type=int, default=-1, help="transducer table copies in the sync kernel (log2; -1 = auto)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe", "fsm"],
                     help="sync kernel A/B")
     ap.add_argument("--cpu-sample-log2", type=int, default=27)
@@ -371,6 +372,7 @@ def main():
     ctx = hb.Context(local, stream=torch.cuda.current_stream().cuda_stream,
                      words_per_thread=args.wpt, ctas_per_sm=args.ctas_per_sm)
     ctx.set_sync_path(args.sync_path)
+    ctx.set_sync_copies(args.sync_copies_log2)
     if args.host_chunk_mib:
         ctx.set_host_chunk(args.host_chunk_mib << 20)
     ctx.set_emit_path(args.emit_path)

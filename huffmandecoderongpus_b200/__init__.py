@@ -114,6 +114,7 @@ def lib():
     L.hb_ctx_set_sync_path.argtypes = [vp, i32]
     L.hb_ctx_set_phase_timing.argtypes = [vp, i32]
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.hb_ctx_set_sync_copies.argtypes = [vp, i32]
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_set_emit_table.argtypes = [vp, i32, i32]
     L.hb_ctx_set_shard_origin.argtypes = [vp, u64, i32]
@@ -306,6 +307,10 @@ class Context:
         """"auto", "always" or "never": whether decodes record the per-phase events."""
         _check(lib().hb_ctx_set_phase_timing(self.h, {"auto": 0, "always": 1, "never": 2}[mode]),
                "hb_ctx_set_phase_timing")
+
+    def set_sync_copies(self, log2_copies=-1):
+        """copies of the transducer table in the sync kernel (log2: 0, 1, 2; -1 = automatic)"""
+        _check(lib().hb_ctx_set_sync_copies(self.h, log2_copies), "hb_ctx_set_sync_copies")
 
     def set_emit_path(self, path):
         """emit kernel: "bytes" (byte stores), "words" (whole 32-bit words, one loop per stream

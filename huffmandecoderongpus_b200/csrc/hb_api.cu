@@ -37,6 +37,8 @@ struct hb_ctx {
     int sync_path = HB_SYNC_AUTO;
     int emit_path = HB_EMIT_AUTO;
     int ep_wf = 0, ep_rshift = -1;   /* EP-/E32-table geometry of the flat / 32-bit emit kernels (0 / -1 = automatic) */
+    int fsm_copies = -1;             /* transducer table copies in the sync kernel: log2; -1 = automatic = one (measured: 4 copies
+                                      * in one 1024-thread CTA 0.494 ms against 0.438 ms with one copy per CTA and 48 warps per SM) */
     uint32_t smem_base = 0x400;      /* shared-window address at which a kernel's dynamic shared memory begins (measured) */
     int phase_timing = HB_PHASES_AUTO;
     bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
@@ -216,6 +218,12 @@ extern "C" int hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_
 extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
     if (!ctx || path < HB_SYNC_AUTO || path > HB_SYNC_FSM) return HB_ERR_ARG;
     ctx->sync_path = path;
+    return HB_OK;
+}
+
+extern "C" int hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies) {
+    if (!ctx || log2_copies < -1 || log2_copies > 2) return HB_ERR_ARG;
+    ctx->fsm_copies = log2_copies;
     return HB_OK;
 }
 
@@ -483,24 +491,24 @@ static bool phase_events(const hb_ctx *ctx, uint32_t ntiles) {
 
 /* Transducer sync kernel over tiles [0, n_full).  G groups of HB_T threads share one
  * table copy per CTA; G is chosen for the most resident warps per SM. */
-template <int WPT, int G>
-static int try_fsm_geometry(hb_ctx *ctx, size_t table_bytes, int *occ, size_t *smem) {
-    *smem = table_bytes + (size_t)G * hb_fsm_group_words<WPT>() * sizeof(uint32_t);
+template <int WPT, int G, int LC>
+static int try_fsm_geometry(hb_ctx *ctx, size_t table_bytes, size_t extra_bytes, int *occ, size_t *smem) {
+    *smem = (table_bytes << LC) + extra_bytes + (size_t)G * hb_fsm_group_words<WPT>() * sizeof(uint32_t);
     *occ = 0;
     if (*smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return HB_OK;
-    CK(cudaFuncSetAttribute(hb_fsm_sync_kernel<WPT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hb_fsm_sync_kernel<WPT, G>, G * HB_T, *smem));
+    CK(cudaFuncSetAttribute(hb_fsm_sync_kernel<WPT, G, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hb_fsm_sync_kernel<WPT, G, LC>, G * HB_T, *smem));
     return HB_OK;
 }
 
-template <int WPT, int G>
+template <int WPT, int G, int LC>
 static int run_fsm_sync(hb_ctx *ctx, const hb_stream_args &a, const hb_fsm_args &fa, uint32_t n_full,
                         int occ, size_t smem) {
     if (ctx->ctas_per_sm > 0 && ctx->ctas_per_sm < occ) occ = ctx->ctas_per_sm;
     uint64_t grid = (uint64_t)occ * (uint64_t)ctx->prop.multiProcessorCount;
     const uint64_t need = ((uint64_t)n_full + G - 1) / G;
     if (grid > need) grid = need;
-    hb_fsm_sync_kernel<WPT, G><<<(int)grid, G * HB_T, smem, ctx->stream>>>(
+    hb_fsm_sync_kernel<WPT, G, LC><<<(int)grid, G * HB_T, smem, ctx->stream>>>(
         a, fa, n_full, (uint16_t *)ctx->subs.p, (uint32_t *)ctx->tmaps.p);
     CK(cudaGetLastError());
     ctx->last_launches++;
@@ -515,12 +523,28 @@ static int launch_fsm_sync(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_a
     fa.depth = cb->d_fsm + ns * 512;
     fa.pstep = (const uint16_t *)(cb->d_fsm + ns * 512 + 256);
     fa.nstates = (uint32_t)ns;
-    const size_t table_bytes = ns * 512 + 256 + 512;
-    int occ[3] = {0, 0, 0}, rc;
+    const size_t table_bytes = ns * 512, extra = 256 + 512;
+    int rc;
+    /* on request (A/B, tests): two or four copies of the table on disjoint banks, one CTA of four groups
+     * per SM, 8-word subsequences.  Fewer bank-conflict replays, but 32 instead of 48 warps per SM, and the
+     * walk is a chain of dependent lookups that needs the warps: measured slower, never automatic. */
+    if (WPT == 8 && ctx->fsm_copies > 0) {
+        int occ = 0;
+        size_t smem = 0;
+        if (ctx->fsm_copies != 1) {
+            if ((rc = try_fsm_geometry<8, 4, 2>(ctx, table_bytes, extra, &occ, &smem))) return rc;
+            if (occ > 0) return run_fsm_sync<8, 4, 2>(ctx, a, fa, n_full, occ, smem);
+        }
+        if (ctx->fsm_copies == 1) {
+            if ((rc = try_fsm_geometry<8, 4, 1>(ctx, table_bytes, extra, &occ, &smem))) return rc;
+            if (occ > 0) return run_fsm_sync<8, 4, 1>(ctx, a, fa, n_full, occ, smem);
+        }
+    }
+    int occ[3] = {0, 0, 0};
     size_t smem[3] = {0, 0, 0};
-    if ((rc = try_fsm_geometry<WPT, 1>(ctx, table_bytes, &occ[0], &smem[0]))) return rc;
-    if ((rc = try_fsm_geometry<WPT, 2>(ctx, table_bytes, &occ[1], &smem[1]))) return rc;
-    if ((rc = try_fsm_geometry<WPT, 4>(ctx, table_bytes, &occ[2], &smem[2]))) return rc;
+    if ((rc = try_fsm_geometry<WPT, 1, 0>(ctx, table_bytes, extra, &occ[0], &smem[0]))) return rc;
+    if ((rc = try_fsm_geometry<WPT, 2, 0>(ctx, table_bytes, extra, &occ[1], &smem[1]))) return rc;
+    if ((rc = try_fsm_geometry<WPT, 4, 0>(ctx, table_bytes, extra, &occ[2], &smem[2]))) return rc;
     /* most resident warps; on a tie the larger group count (fewer table copies) */
     int best = -1, best_warps = 0;
     for (int i = 0; i < 3; i++) {
@@ -528,11 +552,11 @@ static int launch_fsm_sync(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_a
         if (warps >= best_warps && warps > 0) { best = i; best_warps = warps; }
     }
     switch (best) {
-    case 0: return run_fsm_sync<WPT, 1>(ctx, a, fa, n_full, occ[0], smem[0]);
-    case 1: return run_fsm_sync<WPT, 2>(ctx, a, fa, n_full, occ[1], smem[1]);
-    case 2: return run_fsm_sync<WPT, 4>(ctx, a, fa, n_full, occ[2], smem[2]);
+    case 0: return run_fsm_sync<WPT, 1, 0>(ctx, a, fa, n_full, occ[0], smem[0]);
+    case 1: return run_fsm_sync<WPT, 2, 0>(ctx, a, fa, n_full, occ[1], smem[1]);
+    case 2: return run_fsm_sync<WPT, 4, 0>(ctx, a, fa, n_full, occ[2], smem[2]);
     }
-    snprintf(ctx->err, sizeof(ctx->err), "transducer table (%zu B) does not fit an SM", table_bytes);
+    snprintf(ctx->err, sizeof(ctx->err), "transducer table (%zu B) does not fit an SM", table_bytes + extra);
     return HB_ERR_CUDA;
 }
 
@@ -729,30 +753,39 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
                      (ctx->emit_path == HB_EMIT_AUTO && cb->lut.wf64 == HB_WF_MAX &&   /* short codes: four symbols per probe pay (fib4g 1.75 vs 1.85 ms) */
                       a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount))) {
         constexpr uint32_t G = 4;
-        /* index width: 14 bits (2.65 symbols per probe on English text against 2.3 with 12, a tenth of
-         * the long-codeword fallbacks) where the 16 K-entry table is worth building: every CTA builds
-         * its own copy, ~10 us, so only from 16 tiles per SM on */
-        uint32_t wf32 = a.ntiles - tile0 >= 16u * (uint32_t)ctx->prop.multiProcessorCount ? 14u : 12u;
+        /* index width: every CTA builds its own table (~0.5 us per 1 K entries), so the wide ones only where
+         * the stream pays for them.  English text: 2.3 symbols per probe with 12 bits, 2.65 with 14, 2.8
+         * with 15, and a tenth of the long-codeword fallbacks (english1g emit 0.723 / 0.651 / 0.641 ms). */
+        const uint32_t per_sm = (a.ntiles - tile0) / (uint32_t)ctx->prop.multiProcessorCount;
+        uint32_t wf32 = per_sm >= 64u ? 15u : (per_sm >= 16u ? 14u : 12u);
         if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
         if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;   /* no longer codeword exists */
-        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : (wf32 >= 14u ? 0u : (wf32 == 13u ? 1u : 2u));
+        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : (wf32 >= 14u ? 0u : (wf32 == 13u ? 1u : 2u));   /* copies: what fits 64 KB (no measurable effect: not bound by replays) */
         const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
         const size_t grp = sizeof(uint32_t) * (size_t)hb_emitw_group_words(stage);
         for (;; rs--) {
             const size_t tab = (size_t)4 << (wf32 + rs);
+            /* aligned to its size when a multiple of it lies inside the window (up to 64 KB); else at offset 0 */
             const size_t abs0 = ((size_t)ctx->smem_base + tab - 1) / tab * tab;
-            const size_t tab_off = abs0 - ctx->smem_base;
+            const bool add = abs0 + tab > (size_t)ctx->smem_base + limit;
+            const size_t tab_off = add ? 0 : abs0 - ctx->smem_base;
             size_t n_before = tab_off / grp;
             if (n_before > G) n_before = G;
             const size_t total = tab_off + tab + (G - n_before) * grp;
             if (total <= limit) {
                 ae.wf = wf32;
                 const uint32_t need = (a.ntiles - tile0 + G - 1u) / G;
-                if ((rc = grid_for(ctx, hb_emit32_kernel<WPT, G>, total, need, &grid, G * HB_T))) return rc;
-                hb_emit32_kernel<WPT, G><<<grid, G * HB_T, total, ctx->stream>>>(
-                    ae, tile0, rs, (uint32_t)tab_off, (uint32_t)n_before, (const uint16_t *)ctx->subs.p,
-                    (const uint64_t *)ctx->tile_base.p, (const uint64_t *)(misc + 32), (uint8_t *)d_out,
-                    out_capacity, win, stage, (uint32_t *)(misc + 36));
+#define HB_LAUNCH_EMIT32(ADD)                                                                                  \
+                do {                                                                                           \
+                    if ((rc = grid_for(ctx, hb_emit32_kernel<WPT, G, ADD>, total, need, &grid, G * HB_T))) return rc;   \
+                    hb_emit32_kernel<WPT, G, ADD><<<grid, G * HB_T, total, ctx->stream>>>(                     \
+                        ae, tile0, rs, (uint32_t)tab_off, (uint32_t)n_before, (const uint16_t *)ctx->subs.p,  \
+                        (const uint64_t *)ctx->tile_base.p, (const uint64_t *)(misc + 32), (uint8_t *)d_out,   \
+                        out_capacity, win, stage, (uint32_t *)(misc + 36));                                    \
+                } while (0)
+                if (add) HB_LAUNCH_EMIT32(true);
+                else HB_LAUNCH_EMIT32(false);
+#undef HB_LAUNCH_EMIT32
                 done32 = true;
                 break;
             }

@@ -598,6 +598,8 @@ struct hb_tables32 {
                             * entry (copy r of entry x at byte (x << sc) + 4 r) and sit on disjoint banks */
     hb_lutref slow;
     uint32_t sc, wf;
+    uint32_t addbase = 0u; /* device, hb_probe32<true>: the table's address when it cannot be aligned to its size
+                            * (128 KB tables); lanebase then holds the copy offset only */
 };
 
 /* E32 entry of index x (wf bits, LSB first) from the single-symbol table */
@@ -614,11 +616,12 @@ HB_HD uint32_t hb_e32_entry(const hb_lutref &slow, uint32_t x, uint32_t wf) {
     return n ? (syms | (n << 24) | (pos << 26)) : (HB_E64_MARK << 26);
 }
 
+template <bool ADD = false>
 HB_HD uint32_t hb_probe32(const hb_tables32 &tb, uint32_t los, uint32_t his, uint32_t acc) {
     const uint32_t x = (hb_funnel_r(los, his, acc) & tb.fmask) | tb.lanebase;
 #ifdef __CUDA_ARCH__
     uint32_t ent;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(x));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(ADD ? x + tb.addbase : x));
     return ent;
 #else
     return tb.fast[x >> tb.sc];
@@ -633,7 +636,10 @@ HB_HD uint32_t hb_e32_single(const hb_lutref &slow, uint32_t lo, uint32_t hi, ui
 }
 
 HB_HD uint32_t hb_e32_nsym(uint32_t ent) { return (ent >> 24) & 3u; }
-HB_HD uint32_t hb_e32_shift(uint32_t ent) { return (ent >> 21) & 0x18u; }   /* 8 * nsym */
+/* 8 * nsym.  (Taking it with IMAD.HI -- a multiply by 2^11 -- to move work from the integer ALU
+ * pipe, the kernel's busiest unit, to the FMA pipe was measured slower: 0.665 vs 0.650 ms.) */
+HB_HD uint32_t hb_e32_shift(uint32_t ent) { return (ent >> 21) & 0x18u; }
+HB_HD uint32_t hb_e32_advance(uint32_t acc, uint32_t ent) { return acc + (ent >> 26); }
 
 /* shift the first t / 8 symbols of ent into the window; store the staging word they complete */
 HB_HD uint32_t hb_push32(uint32_t ent, uint32_t t, uint32_t &pend, uint32_t posk, hb_out_t &wpp) {
@@ -644,7 +650,7 @@ HB_HD uint32_t hb_push32(uint32_t ent, uint32_t t, uint32_t &pend, uint32_t posk
     return posk_n;
 }
 
-template <int WPT>
+template <int WPT, bool ADD = false>
 HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
                               uint32_t c, hb_out_t out, uint32_t mis) {
     const uint32_t SC = tb.sc;
@@ -656,16 +662,16 @@ HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1
         const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
         for (;;) {
             do {
-                const uint32_t ent = hb_probe32(tb, los, his, acc);
+                const uint32_t ent = hb_probe32<ADD>(tb, los, his, acc);
                 posk = hb_push32(ent, hb_e32_shift(ent), pend, posk, wpp);
-                acc += ent >> 26;
+                acc = hb_e32_advance(acc, ent);
             } while (!(acc & 0xE0u));
             if (acc < HB_E64_MARK) break;
             /* the last entry was the marker: a codeword longer than the index starts there */
             acc -= HB_E64_MARK;
             const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
             posk = hb_push32(ent, 8u, pend, posk, wpp);
-            acc += ent >> 26;
+            acc = hb_e32_advance(acc, ent);
             if (acc & 0xE0u) break;
         }
         acc -= 32u;
@@ -680,36 +686,36 @@ HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1
         for (;;) {
             if (acc <= safe) {
                 do {
-                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    const uint32_t ent = hb_probe32<ADD>(tb, los, his, acc);
                     posk = hb_push32(ent, hb_e32_shift(ent), pend, posk, wpp);
-                    acc += ent >> 26;
+                    acc = hb_e32_advance(acc, ent);
                 } while (acc <= safe);
             }
             if (acc < HB_E64_MARK) break;
             acc -= HB_E64_MARK;              /* a long codeword that starts at or below `safe`: ours */
             const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
             posk = hb_push32(ent, 8u, pend, posk, wpp);
-            acc += ent >> 26;
+            acc = hb_e32_advance(acc, ent);
             if (acc & 0xE0u) { done = true; break; }
         }
         if (!done) {
             uint32_t n = (uint32_t)(wpp - out) + ((posk >> 3) & 3u);   /* symbols pushed so far */
             for (;;) {
                 while (!(acc & 0xE0u)) {
-                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    const uint32_t ent = hb_probe32<ADD>(tb, los, his, acc);
                     const uint32_t ns = hb_e32_nsym(ent);
                     uint32_t t = 8u * ns;
                     if (n + ns > c) t = n < c ? 8u * (c - n) : 0u;
                     posk = hb_push32(ent, t, pend, posk, wpp);
                     n += ns;
-                    acc += ent >> 26;
+                    acc = hb_e32_advance(acc, ent);
                 }
                 if (acc < HB_E64_MARK) break;
                 acc -= HB_E64_MARK;
                 const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
                 posk = hb_push32(ent, n < c ? 8u : 0u, pend, posk, wpp);
                 n += 1u;
-                acc += ent >> 26;
+                acc = hb_e32_advance(acc, ent);
                 if (acc & 0xE0u) break;      /* a long codeword may end past HB_E64_MARK: not a marker */
             }
         }
@@ -722,7 +728,7 @@ HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1
 }
 
 /* Partial subsequence (stream tail): byte stores, every symbol clipped to the chain's count c */
-template <int WPT>
+template <int WPT, bool ADD = false>
 HB_HD uint32_t hb_emit_clipped32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t lim,
                                  uint32_t e, uint32_t c, hb_out_t out) {
     const uint32_t SC = tb.sc;
@@ -734,20 +740,20 @@ HB_HD uint32_t hb_emit_clipped32(const hb_tables32 &tb, const uint32_t (&w)[WPT 
             const uint32_t los = lo << SC, his = hb_funnel_l(lo, hi, SC);
             for (;;) {
                 while (!(acc & 0xE0u)) {
-                    const uint32_t ent = hb_probe32(tb, los, his, acc);
+                    const uint32_t ent = hb_probe32<ADD>(tb, los, his, acc);
                     const uint32_t ns = hb_e32_nsym(ent);
 #pragma unroll
                     for (uint32_t i = 0; i < HB_E32_MAXSYM; i++)
                         if (i < ns && n + i < c) hb_st8(out, n + i, ent >> (8u * i));
                     n += ns;
-                    acc += ent >> 26;
+                    acc = hb_e32_advance(acc, ent);
                 }
                 if (acc < HB_E64_MARK) break;
                 acc -= HB_E64_MARK;
                 const uint32_t ent = hb_e32_single(tb.slow, lo, hi, acc);
                 if (n < c) hb_st8(out, n, ent);
                 n += 1u;
-                acc += ent >> 26;
+                acc = hb_e32_advance(acc, ent);
                 if (acc & 0xE0u) break;
             }
             acc -= 32u;
@@ -1027,7 +1033,97 @@ struct hb_fsm {
     uint32_t tab_saddr;      /* its shared-state-space address (device) */
     const uint8_t *depth;    /* fsm_depth[state] */
     const uint16_t *pstep;   /* fsm_pstep[(1 << r) + bits]: root entry for a step of r < 8 bits */
+    /* device: the table may be held in R = 1 << lc copies on disjoint banks (hb_fsmc_* below);
+     * cbits = this thread's copy index c positioned inside a spread byte, (c << (14 - 2 lc)) * 0x10001 */
+    uint32_t lc = 0u, cbits = 0u;
 };
+
+/* ---- bank-separated copies of the transducer table --------------------------------------
+ * A step's lookup is a random 2-byte read: the 32 lanes of a warp on 32 banks need 3.05
+ * wavefronts on average, and the sync kernel is bound by exactly those (87 % of the L1/shared
+ * data pipe).  With R copies, each confined to 32 / R banks, only the 32 / R lanes of one copy
+ * can collide.  Copy c of entry (state s, byte b) lives at byte
+ *     s * (512 R) + (b >> lo) * 128 + c * (128 / R) + (b & mlo) * 2,     lo = 6 - lc, mlo = 2^lo - 1
+ * (every 128-byte line holds the same 64 / R entries of all R copies).  The address must stay
+ * ONE instruction behind the PRMT that joins state and byte, so every stream word is "spread"
+ * once (8 instructions, kept for the re-walks): byte b becomes the 16-bit field
+ *     V = (b >> lo) << (14 - lc) | c << (14 - 2 lc) | (b & mlo) << (8 - lc),
+ * even bytes of the word in ve, odd bytes in vo.  PRMT then builds X = state << 24 | V << 8 and
+ * the address is base + (X >> (15 - lc)) -- a LEA.HI. */
+template <int LC>
+HB_HD void hb_fsmc_spread(uint32_t w, uint32_t cbits, uint32_t &ve, uint32_t &vo) {
+    constexpr uint32_t lo = 6u - LC, mlo = (1u << lo) - 1u, mhi = 0xffu ^ mlo;
+    constexpr uint32_t LMe = mlo * 0x00010001u, HMe = mhi * 0x00010001u;
+    ve = (w & HMe) * 256u + (w & LMe) * (1u << (8 - LC)) + cbits;      /* multiplies: the FMA pipe is idle */
+    vo = (w & (HMe << 8)) | ((w & (LMe << 8)) >> LC) | cbits;
+}
+
+/* entry for (state in bits 15:8 of ent, byte I of the spread word) */
+template <int LC, int I>
+HB_HD uint32_t hb_fsmc_step(const hb_fsm &f, uint32_t ent, uint32_t ve, uint32_t vo) {
+    const uint32_t v = (I & 1) ? vo : ve;
+#ifdef __CUDA_ARCH__
+    const uint32_t x = __byte_perm(ent, v, (I & 2) ? 0x1760 : 0x1540);   /* state : V : (ends) */
+    uint16_t r;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(f.tab_saddr + (x >> (15 - LC))));
+    return r;
+#else
+    constexpr uint32_t lo = 6u - LC, mlo = (1u << lo) - 1u;
+    const uint32_t vi = (I & 2) ? v >> 16 : v & 0xffffu;
+    const uint32_t b = ((vi >> (14 - LC)) << lo) | ((vi >> (8 - LC)) & mlo);
+    return f.tab[(ent & 0xff00u) | b];
+#endif
+}
+
+template <int LC>
+HB_HD uint32_t hb_fsmc_word(const hb_fsm &f, uint32_t ve, uint32_t vo, uint32_t &ent) {
+    ent = hb_fsmc_step<LC, 0>(f, ent, ve, vo);
+    uint32_t acc = ent;
+    ent = hb_fsmc_step<LC, 1>(f, ent, ve, vo); acc += ent;
+    ent = hb_fsmc_step<LC, 2>(f, ent, ve, vo); acc += ent;
+    ent = hb_fsmc_step<LC, 3>(f, ent, ve, vo); acc += ent;
+    return (ent & 0xff00u) | (acc & 0xffu);
+}
+
+/* v[2 j], v[2 j + 1]: spread word j */
+template <int WPT, int LC>
+HB_HD void hb_fsmc_walk(const hb_fsm &f, const uint32_t (&v)[2 * WPT], uint32_t state, uint32_t (&rec)[WPT]) {
+    uint32_t ent = state << 8;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) rec[j] = hb_fsmc_word<LC>(f, v[2 * j], v[2 * j + 1], ent);
+}
+
+template <int WPT, int LC>
+HB_HD bool hb_fsmc_rewalk(const hb_fsm &f, const uint32_t (&v)[2 * WPT], uint32_t state, uint32_t (&rec)[WPT]) {
+    uint32_t ent = state << 8;
+    bool merged = false;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        if (!merged) {
+            const uint32_t r = hb_fsmc_word<LC>(f, v[2 * j], v[2 * j + 1], ent);
+            merged = ((r ^ rec[j]) & 0xff00u) == 0u;
+            rec[j] = r;
+        }
+    }
+    return !merged;
+}
+
+/* entry (state << 8 | byte) in whatever layout the table has: hypothesis lanes only */
+HB_HD uint32_t hb_fsm_lookup(const hb_fsm &f, uint32_t sb) {
+#ifdef __CUDA_ARCH__
+    uint32_t off = 2u * sb;
+    if (f.lc) {
+        const uint32_t lc = f.lc, lo = 6u - lc, b = sb & 0xffu;
+        const uint32_t c = (f.cbits >> (14u - 2u * lc)) & ((1u << lc) - 1u);
+        off = ((sb >> 8) << (9u + lc)) + ((b >> lo) << 7) + (c << (7u - lc)) + ((b & ((1u << lo) - 1u)) << 1);
+    }
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(f.tab_saddr + off));
+    return v;
+#else
+    return f.tab[sb];
+#endif
+}
 
 /* entry for (state in bits 15:8 of ent, byte i of w) */
 template <int I>
@@ -1112,14 +1208,7 @@ HB_HD uint32_t hb_fsm_hyp_walk(const hb_fsm &f, const hb_lutref &slow, const Wor
         pos += r;
     }
     while (pos & 31u) {
-#ifdef __CUDA_ARCH__
-        uint16_t v;
-        asm("ld.shared.u16 %0, [%1];" : "=h"(v)
-            : "r"(f.tab_saddr + 2u * ((ent & 0xff00u) | ((w0 >> pos) & 0xffu))));
-        ent = v;
-#else
-        ent = f.tab[(ent & 0xff00u) | ((w0 >> pos) & 0xffu)];
-#endif
+        ent = hb_fsm_lookup(f, (ent & 0xff00u) | ((w0 >> pos) & 0xffu));
         n += ent & 0xffu;
         pos += 8u;
     }
@@ -1131,7 +1220,15 @@ HB_HD uint32_t hb_fsm_hyp_walk(const hb_fsm &f, const hb_lutref &slow, const Wor
             return hb_map_pack32(X0, n + E0 - upto + (d0 ? 1u : 0u));
         }
         if (++wi == (uint32_t)(T * WPT)) break;
-        n += hb_frec_ends(hb_fsm_word(f, word(wi), ent));
+        if (f.lc == 0u) n += hb_frec_ends(hb_fsm_word(f, word(wi), ent));
+        else {
+            const uint32_t wv = word(wi);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ent = hb_fsm_lookup(f, (ent & 0xff00u) | ((wv >> (8 * i)) & 0xffu));
+                n += ent & 0xffu;
+            }
+        }
     }
     const uint32_t d = f.depth[hb_frec_state(ent)];
     return hb_map_pack32(hb_fsm_fwd(slow, word(T * WPT - 1), word(T * WPT), d), n + (d ? 1u : 0u));

@@ -387,26 +387,43 @@ __host__ __device__ constexpr uint32_t hb_fsm_group_words() {
     return (uint32_t)(WPT * HB_T / 2 + HB_T + HB_T + 16);
 }
 
-template <int WPT, int G>
+/* LC > 0: the table is held in 1 << LC copies on disjoint banks (hb_fsmc_* in hb_core.cuh): 2.1
+ * instead of 3.05 wavefronts per lookup with four copies, for two more instructions per step. */
+template <int WPT, int G, int LC>
 __global__ void __launch_bounds__(G * HB_T, (G == 1 ? HB_FSM_CTAS1 : (G == 2 ? HB_FSM_CTAS2 : 1)))
 hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
                    uint16_t *__restrict__ subs, uint32_t *__restrict__ tmaps) {
     constexpr int T = HB_T;
     extern __shared__ __align__(16) uint32_t smem[];
-    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem);                  /* nstates * 256 */
-    uint8_t *s_depth = reinterpret_cast<uint8_t *>(smem + fa.nstates * 128u);   /* 256 */
-    uint16_t *s_pstep = reinterpret_cast<uint16_t *>(smem + fa.nstates * 128u + 64u);   /* 256 */
+    constexpr uint32_t R = 1u << LC;
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem);                  /* nstates * 256 entries, R copies */
+    uint8_t *s_depth = reinterpret_cast<uint8_t *>(smem + fa.nstates * 128u * R);   /* 256 */
+    uint16_t *s_pstep = reinterpret_cast<uint16_t *>(smem + fa.nstates * 128u * R + 64u);   /* 256 */
     const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
-    uint32_t *s_grp = smem + fa.nstates * 128u + 192u + g * hb_fsm_group_words<WPT>();
+    uint32_t *s_grp = smem + fa.nstates * 128u * R + 192u + g * hb_fsm_group_words<WPT>();
     uint16_t *s_rec = reinterpret_cast<uint16_t *>(s_grp);                 /* WPT * T records */
     uint32_t *s_cs = s_grp + WPT * T / 2;                                  /* T: prefix of END counts */
     uint32_t *s_exit = s_cs + T;                                           /* T: state behind each subsequence */
     uint32_t *s_warp = s_exit + T;                                         /* 16; [12..15]: X0, exit depth */
 
     {   /* table: 16-byte copies by the whole CTA */
-        const uint4 *src = reinterpret_cast<const uint4 *>(fa.tab);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
-        for (uint32_t i = threadIdx.x; i < fa.nstates * 32u; i += G * T) dst[i] = __ldg(src + i);
+        if constexpr (LC == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(fa.tab);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+            for (uint32_t i = threadIdx.x; i < fa.nstates * 32u; i += G * T) dst[i] = __ldg(src + i);
+        } else {
+            /* copy c of entry (s, b) at 16-bit index s * 256 R + (b >> lo) * 64 + c * (64 / R) + (b & mlo):
+             * 4-byte pairs of entries stay together (lo >= 4) */
+            constexpr uint32_t lo = 6u - LC, mlo = (1u << lo) - 1u;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(fa.tab);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_tab);
+            for (uint32_t i = threadIdx.x; i < fa.nstates * 128u; i += G * T) {
+                const uint32_t v = __ldg(src + i), sb = 2u * i, st = sb >> 8, b = sb & 0xffu;
+                const uint32_t at = st * 256u * R + (b >> lo) * 64u + (b & mlo);
+#pragma unroll
+                for (uint32_t c = 0; c < R; c++) dst[(at + c * (64u / R)) >> 1] = v;
+            }
+        }
         for (uint32_t i = threadIdx.x; i < 256u; i += G * T) {
             s_depth[i] = __ldg(fa.depth + i);
             s_pstep[i] = __ldg(fa.pstep + i);
@@ -418,6 +435,8 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
     f.tab_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_tab));
     f.depth = s_depth;
     f.pstep = s_pstep;
+    f.lc = (uint32_t)LC;
+    f.cbits = LC ? ((t & (R - 1u)) << (14 - 2 * LC)) * 0x10001u : 0u;
     const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
 
     uint32_t tile = blockIdx.x * G + g;
@@ -429,7 +448,14 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
         /* chain of the guess "a codeword starts at bit 0 of my subsequence" */
         uint32_t rec[WPT];
         uint32_t st_in = 0u;
-        hb_fsm_walk<WPT>(f, w, st_in, rec);
+        uint32_t v[LC ? 2 * WPT : 2];          /* spread words (kept for the re-walks) */
+        if constexpr (LC == 0) {
+            hb_fsm_walk<WPT>(f, w, st_in, rec);
+        } else {
+#pragma unroll
+            for (int j = 0; j < WPT; j++) hb_fsmc_spread<LC>(w[j], f.cbits, v[2 * j], v[2 * j + 1]);
+            hb_fsmc_walk<WPT, LC>(f, v, st_in, rec);
+        }
         s_exit[t] = hb_frec_state(rec[WPT - 1]);
         hb_group_sync(bar);
 
@@ -441,7 +467,8 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
                 const uint32_t sn = s_exit[t - 1];
                 if (sn != st_in) {
                     st_in = sn;
-                    changed = hb_fsm_rewalk<WPT>(f, w, st_in, rec);
+                    if constexpr (LC == 0) changed = hb_fsm_rewalk<WPT>(f, w, st_in, rec);
+                    else changed = hb_fsmc_rewalk<WPT, LC>(f, v, st_in, rec);
                 }
             }
             if (!hb_group_or(bar, changed)) break;
@@ -978,7 +1005,8 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, const uint16_
  *     LOP3 and the probe's address needs no add.  The groups' staging buffers fill the room in
  *     front of the table first (n_before of them), the rest follow it. */
 #define HB_ST_LAYOUT 2u       /* the E32-table is not aligned to its size: host / device layout mismatch */
-template <int WPT, int G>
+/* ADD: a table too large to be aligned to its size (15 index bits, 128 KB): at offset 0, one add per probe */
+template <int WPT, int G, bool ADD>
 __global__ void __launch_bounds__(G * HB_T, HB_EMITW_MIN_CTAS / G)
 hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab_off, uint32_t n_before,
                  const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
@@ -995,7 +1023,7 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
     uint32_t *s_warp = smem + (g < n_before ? g * grp : (tab_off + tab_bytes) / 4u + (g - n_before) * grp);   /* 16 */
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_warp + 16);   /* staging, 16-aligned */
     const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
-    if (tab_saddr & (tab_bytes - 1u)) {
+    if (!ADD && (tab_saddr & (tab_bytes - 1u))) {
         if (threadIdx.x == 0) atomicOr(status, HB_ST_LAYOUT);
         return;
     }
@@ -1010,7 +1038,8 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
     tb.sc = 2u + rshift;
     tb.wf = a.wf;
     tb.fmask = ((1u << a.wf) - 1u) << tb.sc;
-    tb.lanebase = hb_opaque(tab_saddr | ((t & ((1u << rshift) - 1u)) << 2));
+    tb.lanebase = hb_opaque((ADD ? 0u : tab_saddr) | ((t & ((1u << rshift) - 1u)) << 2));
+    tb.addbase = hb_opaque(tab_saddr);
     tb.slow = slow;
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
@@ -1058,8 +1087,8 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
             tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim != S) hb_emit_clipped32<WPT>(tb, w, lim, e, c, dst);
-                else tl = hb_emit_words32<WPT>(tb, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                if (lim != S) hb_emit_clipped32<WPT, ADD>(tb, w, lim, e, c, dst);
+                else tl = hb_emit_words32<WPT, ADD>(tb, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
                 if (o + c - wb >= win && o + c < nk) *s_hi = o + c;
             }
             if (last_win && next < a.ntiles) {

@@ -92,6 +92,10 @@ int  hb_ctx_configure(hb_ctx *ctx, int words_per_thread, int ctas_per_sm);
 #define HB_SYNC_PROBE 1
 #define HB_SYNC_FSM   2
 int  hb_ctx_set_sync_path(hb_ctx *ctx, int path);
+/* Copies of the transducer table in the sync kernel's shared memory, each on its own banks (fewer
+ * bank-conflict replays): log2 of the count, 0 / 1 / 2, or -1 = automatic (four copies when the
+ * table is small enough and the stream large enough).  A/B knob. */
+int  hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies);
 /* How the emit kernel fills its staging buffer:
  *   HB_EMIT_WORDS   whole 32-bit words assembled in registers, up to four symbols per table
  *                   probe (hb_emitw_kernel)

@@ -179,6 +179,18 @@ struct Emul {
             load(tbase + (uint64_t)t * WPT, w);
             for (int j = 0; j <= WPT; j++) W[t][j] = w[j];
             hb_fsm_walk<WPT>(fsm, w, 0u, rec);
+            {   /* the walks over bank-separated table copies (2 and 4 copies, this thread's copy index
+                 * inside the spread bytes) read the same entries */
+                uint32_t v1[2 * WPT], v2[2 * WPT], r1[WPT], r2[WPT];
+                const uint32_t c1 = ((uint32_t)t & 1u) << 12, c2 = ((uint32_t)t & 3u) << 10;
+                for (int j = 0; j < WPT; j++) {
+                    hb_fsmc_spread<1>(w[j], c1 * 0x10001u, v1[2 * j], v1[2 * j + 1]);
+                    hb_fsmc_spread<2>(w[j], c2 * 0x10001u, v2[2 * j], v2[2 * j + 1]);
+                }
+                hb_fsmc_walk<WPT, 1>(fsm, v1, 0u, r1);
+                hb_fsmc_walk<WPT, 2>(fsm, v2, 0u, r2);
+                for (int j = 0; j < WPT; j++) if (r1[j] != rec[j] || r2[j] != rec[j]) fsm_mismatch++;
+            }
             for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
             s_exit[t] = hb_frec_state(rec[WPT - 1]);
         }
@@ -193,7 +205,18 @@ struct Emul {
                     uint32_t w[WPT + 1], rec[WPT];
                     for (int j = 0; j <= WPT; j++) w[j] = W[t][j];
                     for (int j = 0; j < WPT; j++) rec[j] = R[t][j];
-                    if (hb_fsm_rewalk<WPT>(fsm, w, sn, rec)) any = true;
+                    {
+                        uint32_t v2[2 * WPT], r2[WPT];
+                        for (int j = 0; j < WPT; j++) {
+                            hb_fsmc_spread<2>(w[j], (((uint32_t)t & 3u) << 10) * 0x10001u, v2[2 * j], v2[2 * j + 1]);
+                            r2[j] = rec[j];
+                        }
+                        const bool ch2 = hb_fsmc_rewalk<WPT, 2>(fsm, v2, sn, r2);
+                        const bool ch = hb_fsm_rewalk<WPT>(fsm, w, sn, rec);
+                        if (ch != ch2) fsm_mismatch++;
+                        for (int j = 0; j < WPT; j++) if (r2[j] != rec[j]) fsm_mismatch++;
+                        if (ch) any = true;
+                    }
                     for (int j = 0; j < WPT; j++) R[t][j] = rec[j];
                     new_exit[t] = hb_frec_state(rec[WPT - 1]);
                 }

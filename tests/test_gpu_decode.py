@@ -343,9 +343,11 @@ def test_sync_paths_agree(dev, name, wpt):
     must give the same bytes, symbol count and shard map."""
     f = _stream(name)
     outs = []
-    for path in ("fsm", "probe", "auto"):
+    for path in ("fsm", "probe", "auto", "fsm:2", "fsm:1"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
-        c.set_sync_path(path)
+        if ":" in path:      # transducer table in 4 / 2 copies on disjoint banks (8-word subsequences)
+            c.set_sync_copies(int(path.split(":")[1]))
+        c.set_sync_path(path.split(":")[0])
         cb = hb.Codebook(c, f.tree)
         got, res, _ = _decode_dev(c, cb, f, dev)
         comp = _to_dev(f.data, f.nbytes, dev)
@@ -356,7 +358,7 @@ def test_sync_paths_agree(dev, name, wpt):
         cb.close()
         c.close()
     assert O.sha256(outs[0][0]) == O.CORPORA[name][2]
-    for k in (1, 2):
+    for k in (1, 2, 3, 4):
         assert outs[0][1] == outs[k][1] == f.usize
         assert np.array_equal(outs[0][0], outs[k][0])
         assert np.array_equal(outs[0][3], outs[k][3])
@@ -392,7 +394,7 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1"):
+    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         if ":" in path:     # E32-table geometry: index bits, log2(copies)
             _, wf, rs = path.split(":")

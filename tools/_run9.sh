@@ -1,15 +1,15 @@
-O=gpurun_out/r03b; mkdir -p $O
+O=gpurun_out/r03e; mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -3 $O/pytest.log
 B="python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-secondary"
-for v in "--emit-path auto" "--emit-path words32 --ep-wf 13" "--emit-path words32 --ep-wf 12 --ep-copies-log2 0" "--emit-path words32 --ep-wf 14 --ep-copies-log2 0"; do
+for v in "" "--emit-path words32 --ep-wf 15" "--wpt 16" "--wpt 16 --emit-path words32 --ep-wf 15" "--wpt 4"; do
   echo "== english1g $v" >> $O/ab.log; $B $v >> $O/ab.log 2>&1
 done
-for v in "--emit-path auto" "--emit-path words" "--emit-path words32 --ep-wf 13" "--emit-path words32 --ep-wf 12 --ep-copies-log2 0"; do
+for v in "" "--wpt 16"; do
   echo "== fib4g $v" >> $O/ab.log; $B --workload fib4g $v >> $O/ab.log 2>&1
 done
 python - <<'PY'
 import json
-for l in open('gpurun_out/r03b/ab.log'):
+for l in open('gpurun_out/r03e/ab.log'):
     if l.startswith('=='): print(l.strip()); continue
     if l.startswith('{'):
         d=json.loads(l); print('   ms/step %.4f  GB/s %.1f  kernels %s' % (d['ms_per_step'], d['value'], d['roofline']['kernel_ms']))
