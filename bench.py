@@ -256,6 +256,9 @@ class Job:
 
     def step(self, want_result=False):
         hb, c = self.hb, self.comp
+        if self.world == 1:    # one GPU, one shard: the single-GPU entry point
+            return hb.decode_device(self.ctx, self.cb, c.data_ptr(), c.numel(), self.bits_own,
+                                    self.out.data_ptr(), self.cap, want_result=want_result)
         hb.shard_map(self.ctx, self.cb, c.data_ptr(), c.numel(), self.bits_own, self.bits_avail, self.my_map.data_ptr())
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.all_maps, self.my_map)

@@ -415,12 +415,13 @@ def _res_dict(r: Result):
 
 
 def decode_device(ctx: Context, cb: Codebook, d_comp: int, comp_bytes: int, bits: int,
-                  d_out: int, out_capacity: int):
-    """hb_decode_device on raw device pointers (e.g. torch tensor .data_ptr())."""
+                  d_out: int, out_capacity: int, want_result=True):
+    """hb_decode_device on raw device pointers (e.g. torch tensor .data_ptr()).  want_result=False:
+    the kernels are queued and nothing is read back (no host synchronisation)."""
     r = Result()
     _check(lib().hb_decode_device(ctx.h, cb.h, d_comp, comp_bytes, bits, d_out, out_capacity,
-                                  C.byref(r)), "hb_decode_device", ctx.h)
-    return _res_dict(r)
+                                  C.byref(r) if want_result else None), "hb_decode_device", ctx.h)
+    return _res_dict(r) if want_result else None
 
 
 def shard_map(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_map):

@@ -20,6 +20,9 @@ struct hb_codebook {
     uint32_t *d_lut;
     uint8_t *d_fsm;    /* [fsm u16 x states*256][depth u8 x 256][pstep u16 x 256], or NULL */
     double implied_avg_len;   /* sum over leaves of 2^-len * len */
+    /* E32-tables of hb_emit32_kernel, one per index width, built on the device on first use (by a kernel,
+     * stream-ordered) and kept: the emit CTAs then only copy theirs from L2 */
+    uint32_t *d_e32[HB_E32_WF_MAX + 1] = {};
 };
 
 struct hb_buf {
@@ -43,6 +46,7 @@ struct hb_ctx {
     int phase_timing = HB_PHASES_AUTO;
     bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
     bool map_fused = false;       /* the last hb_shard_map left up/top to hb_scan_small_kernel */
+    bool map_notop = false;       /* ... skipped hb_scan_top_kernel: hb_scan_downfix_kernel follows the one chain itself */
     uint32_t last_launches = 0;   /* kernels launched by the last map + emit pair */
     cudaEvent_t ev0[HB_NEV];   /* default event set */
     cudaEvent_t *ev = nullptr; /* set used by the current step */
@@ -359,6 +363,7 @@ extern "C" void hb_codebook_destroy(hb_codebook *cb) {
     if (!cb) return;
     cudaSetDevice(cb->ctx->device);
     if (cb->d_lut) cudaFreeAsync(cb->d_lut, cb->ctx->stream);   /* d_fsm lives in the same allocation */
+    for (uint32_t *p : cb->d_e32) if (p) cudaFreeAsync(p, cb->ctx->stream);
     hb_lut_free(&cb->lut);
     delete cb;
 }
@@ -611,15 +616,19 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
     if (split) CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
     if (phase_events(ctx, a.ntiles)) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->map_fused = ctx->fuse_small && ncta == 1 && !d_map;
+    ctx->map_notop = ctx->fuse_small && ncta > 1 && ncta <= HB_NOTOP_MAX_CTAS && !d_map;
     if (!ctx->map_fused) {
         hb_scan_up_kernel<<<ncta, HB_SCAN_T, 0, ctx->stream>>>((const uint32_t *)ctx->tmaps.p, a.ntiles,
                                                               (uint64_t *)ctx->wmaps.p,
                                                               (uint64_t *)ctx->cmaps.p);
         CK(cudaGetLastError());
-        hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
-                                                      (uint64_t *)ctx->cprefix.p, misc_words(ctx));
-        CK(cudaGetLastError());
-        ctx->last_launches += 2;
+        ctx->last_launches++;
+        if (!ctx->map_notop) {
+            hb_scan_top_kernel<<<1, 32, 0, ctx->stream>>>((const uint64_t *)ctx->cmaps.p, ncta,
+                                                          (uint64_t *)ctx->cprefix.p, misc_words(ctx));
+            CK(cudaGetLastError());
+            ctx->last_launches++;
+        }
     }
     if (d_map)
         CK(cudaMemcpyAsync(d_map, misc_words(ctx), 32 * sizeof(uint64_t), cudaMemcpyDeviceToDevice,
@@ -692,6 +701,28 @@ static int launch_emit_flat(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_
     return rc;
 }
 
+__global__ void __launch_bounds__(256)
+hb_build_e32_kernel(const uint32_t *__restrict__ lut, uint32_t w1, uint32_t wf, uint32_t *__restrict__ out) {
+    const uint32_t x = blockIdx.x * 256u + threadIdx.x;
+    if (x >> wf) return;
+    const hb_lutref slow{lut, lut, (1u << w1) - 1u};
+    out[x] = hb_e32_entry(slow, x, wf);
+}
+
+/* the codebook's E32-table of index width wf (built on first use, on the context's stream) */
+static int e32_table(hb_ctx *ctx, const hb_codebook *cb, uint32_t wf, const uint32_t **out) {
+    hb_codebook *m = const_cast<hb_codebook *>(cb);     /* a cache: not part of the codebook's value */
+    if (!m->d_e32[wf]) {
+        uint32_t *p = nullptr;
+        CK(cudaMallocAsync((void **)&p, sizeof(uint32_t) << wf, ctx->stream));
+        hb_build_e32_kernel<<<((1u << wf) + 255u) / 256u, 256, 0, ctx->stream>>>(cb->d_lut, cb->lut.w1, wf, p);
+        CK(cudaGetLastError());
+        m->d_e32[wf] = p;
+    }
+    *out = m->d_e32[wf];
+    return HB_OK;
+}
+
 template <int WPT>
 static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &a,
                        const uint64_t *d_entry_base, void *d_out, uint64_t out_capacity) {
@@ -715,10 +746,15 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
         }
     } else {
         /* down-sweep; the owner of a tile whose true entry offset is not 0 re-chains its head */
-        hb_scan_downfix_kernel<WPT><<<ncta, HB_SCAN_T, 0, ctx->stream>>>(
+        const size_t cm_bytes = ctx->map_notop ? (size_t)ncta * 32 * sizeof(uint64_t) : 0;
+        if (cm_bytes)
+            CK(cudaFuncSetAttribute(hb_scan_downfix_kernel<WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    HB_NOTOP_MAX_CTAS * 32 * (int)sizeof(uint64_t)));
+        hb_scan_downfix_kernel<WPT><<<ncta, HB_SCAN_T, cm_bytes, ctx->stream>>>(
             a, (const uint32_t *)ctx->tmaps.p, (const uint64_t *)ctx->wmaps.p,
             (const uint64_t *)ctx->cprefix.p, misc, d_entry_base, (uint8_t *)ctx->tile_entry.p,
-            (uint64_t *)ctx->tile_base.p, misc + 32, (uint16_t *)ctx->subs.p);
+            (uint64_t *)ctx->tile_base.p, misc + 32, (uint16_t *)ctx->subs.p,
+            ctx->map_notop ? (const uint64_t *)ctx->cmaps.p : nullptr);
         CK(cudaGetLastError());
         scan_launches = 1;
         if (a.minlen == a.maxlen) {
@@ -753,11 +789,11 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
                      (ctx->emit_path == HB_EMIT_AUTO && cb->lut.wf64 == HB_WF_MAX &&   /* short codes: four symbols per probe pay (fib4g 1.75 vs 1.85 ms) */
                       a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount))) {
         constexpr uint32_t G = 4;
-        /* index width: every CTA builds its own table (~0.5 us per 1 K entries), so the wide ones only where
-         * the stream pays for them.  English text: 2.3 symbols per probe with 12 bits, 2.65 with 14, 2.8
+        /* index width: the table is built once per codebook and width (e32_table) and every CTA copies
+         * it from L2 (4 .. 128 KB).  English text: 2.3 symbols per probe with 12 bits, 2.65 with 14, 2.8
          * with 15, and a tenth of the long-codeword fallbacks (english1g emit 0.723 / 0.651 / 0.641 ms). */
         const uint32_t per_sm = (a.ntiles - tile0) / (uint32_t)ctx->prop.multiProcessorCount;
-        uint32_t wf32 = per_sm >= 64u ? 15u : (per_sm >= 16u ? 14u : 12u);
+        uint32_t wf32 = per_sm >= 32u ? 15u : (per_sm >= 8u ? 14u : 12u);
         if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
         if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;   /* no longer codeword exists */
         uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : (wf32 >= 14u ? 0u : (wf32 == 13u ? 1u : 2u));   /* copies: what fits 64 KB (no measurable effect: not bound by replays) */
@@ -774,6 +810,7 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
             const size_t total = tab_off + tab + (G - n_before) * grp;
             if (total <= limit) {
                 ae.wf = wf32;
+                if ((rc = e32_table(ctx, cb, wf32, &ae.fast))) return rc;
                 const uint32_t need = (a.ntiles - tile0 + G - 1u) / G;
 #define HB_LAUNCH_EMIT32(ADD)                                                                                  \
                 do {                                                                                           \
@@ -990,9 +1027,7 @@ extern "C" int hb_host_unpin(const void *ptr) {
 extern "C" int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                                 uint64_t comp_bytes, uint64_t bits, void *d_out,
                                 uint64_t out_capacity, hb_result *res) {
-    hb_result local;
-    if (!res) res = &local;
-    if (!ctx) return HB_ERR_ARG;
+    if (!ctx) return HB_ERR_ARG;   /* res == NULL: nothing is read back, the call returns with the kernels queued */
     ctx->fuse_small = true;    /* nobody reads the shard map between the two phases */
     const bool ok0 = ctx->origin_known;
     const uint64_t ob0 = ctx->origin_byte;

@@ -1000,14 +1000,15 @@ HB_HD void hb_fix_entries(const hb_tables &tb, const WordFn &word, uint16_t *sub
         if (hb_sub_entry(sub[t]) == e) break;
         const uint32_t lim = tile_lim - s0 < S ? tile_lim - s0 : S;
         uint32_t acc = e, n = 0, land = e;
-        uint32_t lo = word(t * WPT);
-        for (uint32_t j = 0; j < (uint32_t)WPT; j++) {
-            const uint32_t hi = word(t * WPT + j + 1);
+        uint32_t w[WPT + 1];                 /* all words first: independent loads, one round trip */
+#pragma unroll
+        for (int j = 0; j <= WPT; j++) w[j] = word(t * WPT + j);
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
             uint32_t cnt;
-            if (lim == S) hb_word_fast(tb, lo, hi, acc, land, cnt);
-            else hb_word_slow(tb.slow, lo, hi, hb_bound(lim, j), acc, land, cnt);
+            if (lim == S) hb_word_fast(tb, w[j], w[j + 1], acc, land, cnt);
+            else hb_word_slow(tb.slow, w[j], w[j + 1], hb_bound(lim, (uint32_t)j), acc, land, cnt);
             n += cnt;
-            lo = hi;
         }
         sub[t] = hb_sub_pack(e, n);
         e = land;

@@ -623,6 +623,12 @@ struct hb_tile_words {
  * by the thread that owns the tile (S-table; fixed-length codes: hb_fix_fixed_kernel).
  * result[0] = symbols of this shard, [1] = exit offset, [2] = entry, [3] = base.
  * Launched after hb_scan_top_kernel. */
+/* cmaps != nullptr ("no top" mode; single shard whose map nobody reads between the phases, at most
+ * HB_NOTOP_MAX_CTAS scan CTAs): hb_scan_top_kernel was not launched -- CTA b stages the maps of the
+ * CTAs before it in (dynamic) shared memory and one thread follows the ONE chain that matters, that
+ * of the shard's entry offset, through them (b dependent shared-memory reads instead of a launch);
+ * the last CTA goes on through its own map and writes the result. */
+#define HB_NOTOP_MAX_CTAS 120
 template <int WPT>
 __global__ void __launch_bounds__(HB_SCAN_T)
 hb_scan_downfix_kernel(hb_stream_args a, const uint32_t *__restrict__ tmaps,
@@ -630,12 +636,15 @@ hb_scan_downfix_kernel(hb_stream_args a, const uint32_t *__restrict__ tmaps,
                        const uint64_t *__restrict__ shard_map,
                        const uint64_t *__restrict__ entry_base,
                        uint8_t *__restrict__ tile_entry, uint64_t *__restrict__ tile_base,
-                       uint64_t *__restrict__ result, uint16_t *__restrict__ subs) {
+                       uint64_t *__restrict__ result, uint16_t *__restrict__ subs,
+                       const uint64_t *__restrict__ cmaps) {
     constexpr int T = HB_T;
     constexpr uint32_t TS = T * 32u * WPT;
     __shared__ __align__(16) uint32_t s_fast[1u << HB_WF_MAX];   /* S-table, for the fix step */
     __shared__ uint32_t s_we[32];
     __shared__ uint64_t s_wb[32];
+    __shared__ uint64_t s_cp;
+    extern __shared__ __align__(16) uint64_t s_cm[];              /* "no top" mode: gridDim.x x 32 CTA maps */
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t ntiles = a.ntiles;
     const bool fixed_len = a.minlen == a.maxlen;
@@ -643,8 +652,38 @@ hb_scan_downfix_kernel(hb_stream_args a, const uint32_t *__restrict__ tmaps,
         for (uint32_t i = threadIdx.x; i < (1u << a.wf); i += HB_SCAN_T) s_fast[i] = __ldg(a.fast + i);
     const uint32_t E = entry_base ? (uint32_t)entry_base[0] & 31u : 0u;
     const uint64_t B = entry_base ? entry_base[1] : 0ull;
-    const uint64_t cp = __ldg(cprefix + (uint64_t)blockIdx.x * 32 + E);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint64_t cp;
+    if (cmaps) {
+        const bool last = blockIdx.x == gridDim.x - 1;
+        const uint32_t nrows = blockIdx.x + (last ? 1u : 0u);
+        for (uint32_t i = threadIdx.x; i < nrows * 32u; i += HB_SCAN_T) s_cm[i] = __ldg(cmaps + i);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cur = E;
+            uint64_t n = 0;
+            for (uint32_t c = 0; c < blockIdx.x; c++) {
+                const uint64_t m = s_cm[c * 32u + cur];
+                n += m >> 8;
+                cur = (uint32_t)m & 31u;
+            }
+            s_cp = hb_map_pack64(cur, n);
+            if (last) {
+                const uint64_t m = s_cm[blockIdx.x * 32u + cur];
+                uint64_t total = n + (m >> 8);
+                const uint32_t x = (uint32_t)m & 31u;
+                if (total && a.bits_own + x > a.bits_avail) total--;   /* see below */
+                result[0] = total;
+                result[1] = x;
+                result[2] = E;
+                result[3] = B;
+            }
+        }
+        __syncthreads();
+        cp = s_cp;
+    } else {
+        cp = __ldg(cprefix + (uint64_t)blockIdx.x * 32 + E);
+    }
+    if (!cmaps && blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t sm = shard_map[E];
         uint64_t total = sm >> 8;
         /* the serial decoder emits a symbol only on reaching a leaf: a last
@@ -997,9 +1036,9 @@ hb_emitw_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, const uint16_
 /* Emit kernel with 32-bit table entries (hb_emit_words32 in hb_core.cuh): the default for large
  * streams.  Same tile pipeline as hb_emitw_kernel; the differences are the table and the probe
  * loops.
- *   - The E32-table is built by the CTA itself from the single-symbol table (one thread per index,
- *     R = 1 << rshift copies interleaved entry by entry: copy r on banks r, r + R, ...; lane l reads
- *     copy l & (R - 1), so that only the 32 / R lanes of one copy can collide).
+ *   - The E32-table (a.fast, a.wf index bits; built once per codebook by hb_build_e32_kernel) is copied
+ *     into shared memory in R = 1 << rshift copies interleaved entry by entry: copy r on banks r,
+ *     r + R, ...; lane l reads copy l & (R - 1), so that only the 32 / R lanes of one copy can collide.
  *   - The table sits at a shared-memory address that is a multiple of its size (tab_off, computed
  *     by the host from the dynamic window's base address), so that "base | index | copy" is ONE
  *     LOP3 and the probe's address needs no add.  The groups' staging buffers fill the room in
@@ -1028,9 +1067,15 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
         return;
     }
     const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
-    for (uint32_t x = threadIdx.x; x < (1u << a.wf); x += G * T) {
-        const uint32_t ent = hb_e32_entry(slow, x, a.wf);
-        for (uint32_t r = 0; r < (1u << rshift); r++) s_fast[(x << rshift) + r] = ent;
+    if (rshift == 0u) {       /* one copy: 16-byte vectors */
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.fast);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_fast);
+        for (uint32_t i = threadIdx.x; i < (1u << a.wf) / 4u; i += G * T) dst[i] = __ldg(src + i);
+    } else {
+        for (uint32_t x = threadIdx.x; x < (1u << a.wf); x += G * T) {
+            const uint32_t ent = __ldg(a.fast + x);
+            for (uint32_t r = 0; r < (1u << rshift); r++) s_fast[(x << rshift) + r] = ent;
+        }
     }
     __syncthreads();
     hb_tables32 tb;

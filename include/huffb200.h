@@ -170,7 +170,8 @@ int  hb_codebook_info(const hb_codebook *cb, uint32_t *maxlen, uint32_t *minlen,
 /* d_comp: device pointer, 16-byte aligned, comp_bytes >= ceil(bits/8) readable
  * bytes (the kernels read whole 32-bit words: comp_bytes rounded up to a multiple of 4 must
  * be readable, which any 16-byte-granular allocation gives).  d_out: device pointer with out_capacity bytes.  Runs on the
- * context's stream, synchronises it, and fills *res. */
+ * context's stream, synchronises it, and fills *res.  res == NULL: the kernels are only queued (no
+ * synchronisation, nothing read back; hb_ctx_sync / the next call with a result orders after them). */
 int hb_decode_device(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
                      uint64_t comp_bytes, uint64_t bits, void *d_out,
                      uint64_t out_capacity, hb_result *res);
