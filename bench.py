@@ -397,7 +397,7 @@ def main():
     k_ms = {k: phases[k] / max(phases["steps"], 1) for k in ("sync", "scan", "emit", "total")}
     dom = max(("sync", "emit"), key=lambda k: k_ms[k])
     sync_name = "hb_sync_kernel" if args.sync_path == "probe" else "hb_fsm_sync_kernel"
-    emit_name = {"bytes": "hb_emit_kernel", "flat": "hb_emitf_kernel", "words": "hb_emitw_kernel"}.get(args.emit_path, "hb_emit32_kernel")
+    emit_name = ctx.last_emit_kernel() or "hb_emit_kernel"
     dom_name = {"sync": sync_name, "emit": emit_name}[dom]
     achieved = b_alg / (k_ms[dom] * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this

@@ -115,6 +115,8 @@ def lib():
     L.hb_ctx_set_phase_timing.argtypes = [vp, i32]
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_sync_copies.argtypes = [vp, i32]
+    L.hb_ctx_last_emit_kernel.argtypes = [vp]
+    L.hb_ctx_last_emit_kernel.restype = C.c_char_p
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
     L.hb_ctx_set_emit_table.argtypes = [vp, i32, i32]
     L.hb_ctx_set_shard_origin.argtypes = [vp, u64, i32]
@@ -307,6 +309,10 @@ class Context:
         """"auto", "always" or "never": whether decodes record the per-phase events."""
         _check(lib().hb_ctx_set_phase_timing(self.h, {"auto": 0, "always": 1, "never": 2}[mode]),
                "hb_ctx_set_phase_timing")
+
+    def last_emit_kernel(self):
+        """name of the emit kernel the last decode used for the bulk of its tiles"""
+        return lib().hb_ctx_last_emit_kernel(self.h).decode()
 
     def set_sync_copies(self, log2_copies=-1):
         """copies of the transducer table in the sync kernel (log2: 0, 1, 2; -1 = automatic)"""

@@ -23,6 +23,7 @@ struct hb_codebook {
     /* E32-tables of hb_emit32_kernel, one per index width, built on the device on first use (by a kernel,
      * stream-ordered) and kept: the emit CTAs then only copy theirs from L2 */
     uint32_t *d_e32[HB_E32_WF_MAX + 1] = {};
+    uint32_t *d_e64[HB_E32_WF_MAX + 1] = {};   /* E64-tables of other widths than lut.wf64 (hb_emitw_kernel), same scheme */
 };
 
 struct hb_buf {
@@ -42,12 +43,14 @@ struct hb_ctx {
     int ep_wf = 0, ep_rshift = -1;   /* EP-/E32-table geometry of the flat / 32-bit emit kernels (0 / -1 = automatic) */
     int fsm_copies = -1;             /* transducer table copies in the sync kernel: log2; -1 = automatic = one (measured: 4 copies
                                       * in one 1024-thread CTA 0.494 ms against 0.438 ms with one copy per CTA and 48 warps per SM) */
+    uint32_t e64_wide = 11;          /* E64 index width for short codes in large streams (set from measurements) */
     uint32_t smem_base = 0x400;      /* shared-window address at which a kernel's dynamic shared memory begins (measured) */
     int phase_timing = HB_PHASES_AUTO;
     bool fuse_small = false;      /* set by hb_decode_device: single shard, nobody reads the map between the phases */
     bool map_fused = false;       /* the last hb_shard_map left up/top to hb_scan_small_kernel */
     bool map_notop = false;       /* ... skipped hb_scan_top_kernel: hb_scan_downfix_kernel follows the one chain itself */
     uint32_t last_launches = 0;   /* kernels launched by the last map + emit pair */
+    const char *last_emit = "";   /* the emit kernel the last hb_shard_emit launched for the bulk of the tiles */
     cudaEvent_t ev0[HB_NEV];   /* default event set */
     cudaEvent_t *ev = nullptr; /* set used by the current step */
     cudaEvent_t *tim_ev = nullptr; /* optional ring: tim_cap steps x HB_NEV events */
@@ -225,6 +228,8 @@ extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
     return HB_OK;
 }
 
+extern "C" const char *hb_ctx_last_emit_kernel(const hb_ctx *ctx) { return ctx ? ctx->last_emit : ""; }
+
 extern "C" int hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies) {
     if (!ctx || log2_copies < -1 || log2_copies > 2) return HB_ERR_ARG;
     ctx->fsm_copies = log2_copies;
@@ -364,6 +369,7 @@ extern "C" void hb_codebook_destroy(hb_codebook *cb) {
     cudaSetDevice(cb->ctx->device);
     if (cb->d_lut) cudaFreeAsync(cb->d_lut, cb->ctx->stream);   /* d_fsm lives in the same allocation */
     for (uint32_t *p : cb->d_e32) if (p) cudaFreeAsync(p, cb->ctx->stream);
+    for (uint32_t *p : cb->d_e64) if (p) cudaFreeAsync(p, cb->ctx->stream);
     hb_lut_free(&cb->lut);
     delete cb;
 }
@@ -709,6 +715,27 @@ hb_build_e32_kernel(const uint32_t *__restrict__ lut, uint32_t w1, uint32_t wf, 
     out[x] = hb_e32_entry(slow, x, wf);
 }
 
+__global__ void __launch_bounds__(256)
+hb_build_e64_kernel(const uint32_t *__restrict__ lut, uint32_t w1, uint32_t wf, uint32_t *__restrict__ out) {
+    const uint32_t x = blockIdx.x * 256u + threadIdx.x;
+    if (x >> wf) return;
+    const hb_lutref slow{lut, lut, (1u << w1) - 1u};
+    hb_e64_entry(slow, x, wf, out + 2 * x, out + 2 * x + 1);
+}
+
+static int e64_table(hb_ctx *ctx, const hb_codebook *cb, uint32_t wf, const uint32_t **out) {
+    hb_codebook *m = const_cast<hb_codebook *>(cb);
+    if (!m->d_e64[wf]) {
+        uint32_t *p = nullptr;
+        CK(cudaMallocAsync((void **)&p, sizeof(uint32_t) * 2 << wf, ctx->stream));
+        hb_build_e64_kernel<<<((1u << wf) + 255u) / 256u, 256, 0, ctx->stream>>>(cb->d_lut, cb->lut.w1, wf, p);
+        CK(cudaGetLastError());
+        m->d_e64[wf] = p;
+    }
+    *out = m->d_e64[wf];
+    return HB_OK;
+}
+
 /* the codebook's E32-table of index width wf (built on first use, on the context's stream) */
 static int e32_table(hb_ctx *ctx, const hb_codebook *cb, uint32_t wf, const uint32_t **out) {
     hb_codebook *m = const_cast<hb_codebook *>(cb);     /* a cache: not part of the codebook's value */
@@ -778,7 +805,7 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     if (WPT == 8 && ctx->emit_path == HB_EMIT_FLAT && a.ntiles >= 2) {
         bool launched = false;
         if ((rc = launch_emit_flat(ctx, cb, a, a.ntiles - 1u, d_out, out_capacity, &launched))) return rc;
-        if (launched) { tile0 = a.ntiles - 1u; ctx->last_launches++; }
+        if (launched) { tile0 = a.ntiles - 1u; ctx->last_launches++; ctx->last_emit = "hb_emitf_kernel"; }
     }
     /* staging stores: whole words, three symbols per probe (english1g 0.75 ms vs 0.81 with
      * byte stores); the byte-store kernel on request */
@@ -824,6 +851,7 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
                 else HB_LAUNCH_EMIT32(false);
 #undef HB_LAUNCH_EMIT32
                 done32 = true;
+                ctx->last_emit = "hb_emit32_kernel";
                 break;
             }
             if (rs == 0) break;
@@ -833,17 +861,33 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     } else if (ctx->emit_path != HB_EMIT_BYTES) {
         ae.fast = a.fast + ((size_t)2 << a.wf);   /* E64-table */
         ae.wf = cb->lut.wf64;                     /* ... and its own index width */
-        /* G groups of 256 threads share R = G copies of the table: the same shared memory per
-         * thread as one copy per 256 threads, fewer bank conflicts (hb_tables64).  Streams of
-         * at least two tiles per SM; hb_ctx_set_emit_table's log2_copies overrides (0 / 1 / 2). */
-        uint32_t rs = 0;
+        /* another width on request (hb_ctx_set_emit_table), or 13 bits for short codes in large streams:
+         * 3.6 instead of 3.2 symbols per probe on the Fibonacci-skewed model */
+        uint32_t wfx = ae.wf;
+        if (ctx->ep_wf >= 9 && ctx->ep_wf <= 14) wfx = (uint32_t)ctx->ep_wf;
+        else if (ctx->emit_path == HB_EMIT_AUTO && cb->lut.wf64 < HB_WF_MAX &&
+                 a.ntiles - tile0 >= 32u * (uint32_t)ctx->prop.multiProcessorCount) wfx = ctx->e64_wide;
+        if (wfx > cb->lut.maxlen && cb->lut.maxlen >= 9u) wfx = cb->lut.maxlen;
+        if (wfx != ae.wf) {
+            if ((rc = e64_table(ctx, cb, wfx, &ae.fast))) return rc;
+            ae.wf = wfx;
+        }
+        /* G groups of 256 threads share R copies of the table (hb_tables64) */
         const uint32_t left = a.ntiles - tile0;
-        if (ctx->ep_rshift >= 0) rs = ctx->ep_rshift > 2 ? 2u : (uint32_t)ctx->ep_rshift;
-        else if (left >= 4u * (uint32_t)ctx->prop.multiProcessorCount) rs = 2u;   /* measured: english1g emit 0.775 -> 0.747 ms, fib4g 1.85 -> 1.75 (2 copies: no change) */
         const uint32_t grp = sizeof(uint32_t) * hb_emitw_group_words(stage);
-        /* fewer copies when table + groups would not fit an SM (large staging windows) */
-        while (rs > 0 && ((size_t)8 << (ae.wf + rs)) + ((size_t)grp << rs) > (size_t)ctx->prop.sharedMemPerBlockOptin) rs--;
-        const uint32_t G = 1u << rs;
+        const size_t optin = (size_t)ctx->prop.sharedMemPerBlockOptin;
+        /* groups: 4 (one 1024-thread CTA per SM) for streams of at least four tiles per SM, else 1;
+         * copies: as requested, else 4 (measured: english1g emit 0.775 -> 0.747 ms, fib4g 1.85 -> 1.75;
+         * 2 copies: no change) -- fewer of either when table + groups would not fit an SM */
+        uint32_t G = left >= 4u * (uint32_t)ctx->prop.multiProcessorCount || ctx->ep_rshift > 0 ? 4u : 1u;
+        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 2 ? 2u : (uint32_t)ctx->ep_rshift) : (G == 4u ? 2u : 0u);
+        while (rs > 0 && ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp > optin) rs--;
+        while (G > 1 && ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp > optin) G >>= 1;
+        if (((size_t)8 << ae.wf) + (size_t)grp > optin && ae.wf != cb->lut.wf64) {
+            /* a wide table beside a large staging window (very short codes): the codebook's own width */
+            ae.fast = a.fast + ((size_t)2 << a.wf);
+            ae.wf = cb->lut.wf64;
+        }
         smem = ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp;   /* the table sits in front of the groups */
         const uint32_t need = (left + G - 1u) / G;
 #define HB_LAUNCH_EMITW(GG)                                                                              \
@@ -858,8 +902,10 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
         else if (G == 2) HB_LAUNCH_EMITW(2);
         else HB_LAUNCH_EMITW(1);
 #undef HB_LAUNCH_EMITW
+        if (!tile0) ctx->last_emit = "hb_emitw_kernel";
     } else {
         ae.fast = a.fast + ((size_t)1 << a.wf);   /* E-table */
+        ctx->last_emit = "hb_emit_kernel";
         if ((rc = grid_for(ctx, hb_emit_kernel<WPT>, smem, a.ntiles, &grid))) return rc;
         hb_emit_kernel<WPT><<<grid, HB_T, smem, ctx->stream>>>(
             ae, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,

@@ -419,6 +419,22 @@ HB_HD hb_pe hb_probe_words(const hb_tables64 &tb, uint32_t los, uint32_t his, ui
     return p;
 }
 
+/* E64 entry of index x (wf bits, LSB first) from the single-symbol table (hb_format.h; the same
+ * values hb_build_tables_kernel writes for the codebook's default width) */
+HB_HD void hb_e64_entry(const hb_lutref &slow, uint32_t x, uint32_t wf, uint32_t *lo, uint32_t *hi) {
+    uint32_t pos = 0, n = 0, syms = 0;
+    while (n < HB_E64_MAXSYM && pos < wf) {
+        uint32_t sym;
+        const uint32_t len = hb_probe(slow, x >> pos, 0u, 0u, &sym);
+        if (pos + len > wf) break;           /* would use bits beyond the index */
+        syms |= sym << (8u * n);
+        n++;
+        pos += len;
+    }
+    *lo = syms;
+    *hi = n ? ((0x3210u + 0x1111u * n) | ((8u * n) << 16) | (pos << 26)) : (0x3210u | (HB_E64_MARK << 26));
+}
+
 HB_HD uint32_t hb_pe_nsym(const hb_pe &p) { return (p.inc >> 3) & 7u; }
 
 #ifdef __CUDA_ARCH__

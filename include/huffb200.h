@@ -111,6 +111,8 @@ int  hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies);
 #define HB_EMIT_WORDS32 4 /* hb_emit32_kernel: word stores, 32-bit table entries with up to three symbols, 4
                              (or 8) copies of the table on disjoint banks */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
+/* name of the emit kernel the last decode used for the bulk of its tiles ("" before the first) */
+const char *hb_ctx_last_emit_kernel(const hb_ctx *ctx);
 /* EP-table of the flat emit kernel: index width in bits (8..12, 0 = automatic) and log2 of the
  * number of copies interleaved in shared memory (0..4, -1 = automatic).  A/B knob. */
 int  hb_ctx_set_emit_table(hb_ctx *ctx, int index_bits, int log2_copies);
