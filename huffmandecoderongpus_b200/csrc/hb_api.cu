@@ -586,7 +586,10 @@ static int launch_map(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args &
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     ctx->last_launches = 0;
     uint32_t tile0 = 0;
-    if (ctx->sync_path != HB_SYNC_PROBE && cb->d_fsm && a.minlen != a.maxlen) {
+    /* codes whose lengths share a factor that is not a power of two: the probe kernel, which can start
+     * every subsequence's chain at the first offset of the right residue class (hb_first_entry) */
+    const bool odd_factor = (a.gmod & (a.gmod - 1u)) != 0u;
+    if (ctx->sync_path != HB_SYNC_PROBE && cb->d_fsm && a.minlen != a.maxlen && !odd_factor) {
         /* full tiles: byte-step transducer kernel -- from two waves of tiles on; below
          * that one probe-kernel launch for everything is quicker */
         const uint32_t n_full = (uint32_t)(a.bits_own / ((uint64_t)HB_T * 32u * WPT));

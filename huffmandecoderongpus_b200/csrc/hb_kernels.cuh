@@ -78,6 +78,19 @@ __device__ __forceinline__ bool hb_entry_possible(const hb_stream_args &a, uint3
     return p == 0u;
 }
 
+/* The first offset at which a chain can enter the subsequence that begins sub_bit0 bits into tile
+ * `tile`: the guess the probe sync kernel starts from.  0 unless the code's lengths share a factor
+ * that is not a power of two (hb_stream_args.gmod): subsequences are 32 * WPT bits long, so their
+ * starts wander through the residue classes mod 3, 5, ... and the guess "a codeword starts at my
+ * bit 0" would be in the wrong class most of the time -- chains of different classes never merge,
+ * and the stitch then needs one round per subsequence of the tile (round 2: 5.5 GB/s). */
+__device__ __forceinline__ uint32_t hb_first_entry(const hb_stream_args &a, uint32_t tile, uint32_t tile_bits,
+                                                   uint32_t sub_bit0) {
+    if (a.gmod <= 1u) return 0u;
+    const uint32_t p = (a.gorg + (tile % a.gmod) * (tile_bits % a.gmod) + sub_bit0 % a.gmod) % a.gmod;
+    return p ? a.gmod - p : 0u;
+}
+
 /* device status word bits */
 #define HB_ST_OUTPUT_FULL 1u
 
@@ -180,7 +193,8 @@ hb_sync_kernel(hb_stream_args a, uint32_t tile0, uint16_t *__restrict__ subs, ui
         /* chain of the guess "a codeword starts at offset 0 of my subsequence"
          * (for a fixed-length code the exact offset under tile entry 0 is known) */
         uint32_t rec[WPT];
-        uint32_t e = fixed_len ? hb_fixed_next(0u, a.maxlen, (uint32_t)t * S) - (uint32_t)t * S : 0u;
+        uint32_t e = fixed_len ? hb_fixed_next(0u, a.maxlen, (uint32_t)t * S) - (uint32_t)t * S
+                               : hb_first_entry(a, tile, TS, (uint32_t)t * S);
         hb_walk<WPT>(tb, w, lim, e, rec);
         s_land[t] = hb_rec_land(rec[WPT - 1]);
         __syncthreads();

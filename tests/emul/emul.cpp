@@ -47,6 +47,11 @@ struct Emul {
     bool possible(uint32_t tile, uint32_t e) const {
         return gmod <= 1u || (gorg + (tile % gmod) * (TS % gmod) + e) % gmod == 0u;
     }
+    uint32_t first_entry(uint32_t tile, uint32_t sub_bit0) const {   /* hb_first_entry in hb_kernels.cuh */
+        if (gmod <= 1u) return 0u;
+        const uint32_t p = (gorg + (tile % gmod) * (TS % gmod) + sub_bit0 % gmod) % gmod;
+        return p ? gmod - p : 0u;
+    }
     hb_tables64 tbE64; int emit_mode = 0;   /* 0 byte stores (E-table), 1 word stores (E64-table), 3 word stores (E32-table) */
     hb_tables32 tbE32; std::vector<uint32_t> e32tab;
     bool flat = false;                       /* flat walk (EP-table) on all tiles but the last */
@@ -88,7 +93,8 @@ struct Emul {
             const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
             lim[t] = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
             const bool fixed_len = minlen == maxlen;
-            e[t] = fixed_len ? hb_fixed_next(0u, maxlen, (uint32_t)t * S) - (uint32_t)t * S : 0u;
+            e[t] = fixed_len ? hb_fixed_next(0u, maxlen, (uint32_t)t * S) - (uint32_t)t * S
+                             : first_entry(tile, (uint32_t)t * S);
             hb_walk<WPT>(tbS, w, lim[t], e[t], rec);
             /* cross-check: the multi-symbol walk equals the symbol-by-symbol walk */
             if (lim[t] == S) {
@@ -253,7 +259,8 @@ struct Emul {
 
     /* dispatch of launch_map in hb_api.cu */
     void sync_all() {
-        const bool use_fsm = sync_mode != 0 && have_fsm && minlen != maxlen;
+        const bool odd_factor = (gmod & (gmod - 1u)) != 0u;      /* launch_map: probe kernel only */
+        const bool use_fsm = sync_mode != 0 && have_fsm && minlen != maxlen && !odd_factor;
         const uint32_t n_full = use_fsm ? (uint32_t)(bits_own / TS) : 0u;
         for (uint32_t tile = 0; tile < ntiles; tile++) {
             if (tile < n_full) {
@@ -560,7 +567,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     }
     if (E.st.long_probes >> 63) rc = -100;   /* fast and slow word walks disagreed */
     if (E.fsm_mismatch) rc = -101;           /* transducer and probe sync kernels disagreed */
-    if (sync_mode && E.have_fsm && minlen != maxlen && E.fsm_tiles != bits_own / E.TS) rc = -102;
+    if (sync_mode && E.have_fsm && minlen != maxlen && !(E.gmod & (E.gmod - 1u)) && E.fsm_tiles != bits_own / E.TS) rc = -102;
     if (stats) *stats = E.st;
     return rc;
 }

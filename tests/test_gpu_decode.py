@@ -501,13 +501,11 @@ def test_common_length_factor_is_no_cliff(dev, lengths):
     f, esyms = m.huff_file_cpu(7, n)
     t_eng = best_ms(f.tree, f.data, f.bits, esyms)
     c.close()
-    # An ODD common factor (3, 6 = 2 * 3 ...) is byte-exact but still slow: subsequences are 256
-    # bits long, so their starts wander through the residue classes and the guess "a codeword
-    # starts at bit 0 of my subsequence" is in the wrong class two times out of three
-    # (DESIGN.md "known slow paths"); only the power-of-two part of the factor is exploited.
+    # An ODD common factor (3, 6 = 2 * 3 ...): subsequences are 256 bits long, so their starts wander
+    # through the residue classes; the probe sync kernel starts every chain at the first offset of the
+    # right class (hb_first_entry) -- slower than the transducer kernel, but no cliff (round 2: 35x).
     fast = all(l % 3 for l in lengths)
-    if fast:
-        assert t_code < 2.0 * t_eng, (t_code, t_eng)
+    assert t_code < (2.0 if fast else 4.0) * t_eng, (t_code, t_eng)
     # sharded: every shard knows where it begins in the stream (hb_multi sets the origin)
     mm = hb.Multi(0)
     mm.load(tree, data, bits)
@@ -516,5 +514,4 @@ def test_common_length_factor_is_no_cliff(dev, lengths):
     mm.download(out)
     mm.close()
     assert np.array_equal(out, syms)
-    if fast:
-        assert best < 2.0 * t_eng, (best, t_eng)
+    assert best < (2.0 if fast else 4.0) * t_eng, (best, t_eng)

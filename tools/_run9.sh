@@ -1,13 +1,3 @@
-O=gpurun_out/r03i; mkdir -p $O
-HB_STRESS_SEEDS=12 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -3 $O/pytest.log
-B="python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-secondary"
-echo "== english1g" >> $O/ab.log; $B >> $O/ab.log 2>&1
-echo "== fib4g" >> $O/ab.log; $B --workload fib4g >> $O/ab.log 2>&1
-python - <<'PY'
-import json
-for l in open('gpurun_out/r03i/ab.log'):
-    if l.startswith('=='): print(l.strip()); continue
-    if l.startswith('{'):
-        d=json.loads(l); print('   ms/step %.4f  GB/s %.1f launches %s kernels %s' % (d['ms_per_step'], d['value'], d['gpu_launches'], d['roofline']['kernel_ms']))
-    else: print('   '+l.strip()[:200])
-PY
+O=gpurun_out/r03j; mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -5 $O/pytest.log
+python tools/slow_path_probe.py > $O/slow_paths.txt 2>&1; cat $O/slow_paths.txt
