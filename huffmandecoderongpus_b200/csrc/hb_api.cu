@@ -883,7 +883,7 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
          * copies: as requested, else 4 (measured: english1g emit 0.775 -> 0.747 ms, fib4g 1.85 -> 1.75;
          * 2 copies: no change) -- fewer of either when table + groups would not fit an SM */
         uint32_t G = left >= 4u * (uint32_t)ctx->prop.multiProcessorCount || ctx->ep_rshift > 0 ? 4u : 1u;
-        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 2 ? 2u : (uint32_t)ctx->ep_rshift) : (G == 4u ? 2u : 0u);
+        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : (G == 4u ? 2u : 0u);
         while (rs > 0 && ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp > optin) rs--;
         while (G > 1 && ((size_t)8 << (ae.wf + rs)) + (size_t)G * grp > optin) G >>= 1;
         if (((size_t)8 << ae.wf) + (size_t)grp > optin && ae.wf != cb->lut.wf64) {
