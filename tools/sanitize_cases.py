@@ -19,7 +19,7 @@ names = sys.argv[1:] or ["paper1", "kjv", "ecoli", "world192"]
 for name in names:
     f = hb.HuffFile.load(O.corpus_path(name))
     for sync in ("auto", "fsm", "probe"):
-        for emit in ("words", "bytes", "flat"):
+        for emit in ("words", "words32", "bytes", "flat"):
             c = hb.Context(0)
             c.set_sync_path(sync)
             c.set_emit_path(emit)
@@ -32,7 +32,7 @@ for name in names:
 # a synthetic stream of 2^22 symbols: full tiles through the transducer kernel, chunked host path
 m = hb.Model(0)
 fs, syms = m.huff_file_cpu(0x48554646, 1 << 22)
-for emit in ("words", "flat"):
+for emit in ("words", "words32", "flat"):
     c = hb.Context(0)
     c.set_sync_path("fsm")
     c.set_emit_path(emit)
