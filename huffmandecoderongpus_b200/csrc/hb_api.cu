@@ -78,6 +78,7 @@ struct hb_ctx {
     uint64_t *h_pipe = nullptr;       /* pinned: 32 map words + 4 entry/base words per chunk */
     hb_buf d_eb;
     uint64_t pipe_chunk_bytes = 32ull << 20;
+    bool pipe_chunk_default = true;  /* ... not set by the caller: 64 MiB chunks for streams of at least 512 MiB */
     cudaEvent_t pipe_t0 = nullptr, pipe_t1 = nullptr;
     uint64_t *h_res = nullptr; /* pinned, 8 words */
     uint64_t hs_readable = 0, hs_own = 0, hs_avail = 0;   /* shard of the last hb_shard_map_host */
@@ -269,6 +270,7 @@ extern "C" int hb_ctx_set_shard_origin(hb_ctx *ctx, uint64_t first_byte, int kno
 extern "C" int hb_ctx_set_host_chunk(hb_ctx *ctx, uint64_t bytes) {
     if (!ctx) return HB_ERR_ARG;
     ctx->pipe_chunk_bytes = bytes ? bytes : (32ull << 20);
+    ctx->pipe_chunk_default = bytes == 0;
     return HB_OK;
 }
 
@@ -1122,7 +1124,12 @@ static int decode_host_pipelined_run(hb_ctx *ctx, hb_codebook *cb, const uint8_t
                                      uint8_t *out, uint64_t out_capacity, hb_result *res) {
     const uint64_t nbytes = (bits + 7) / 8;
     const uint64_t tile_bytes = (uint64_t)HB_T * 4u * (uint64_t)ctx->wpt;
-    uint64_t cbytes = ctx->pipe_chunk_bytes / tile_bytes * tile_bytes;
+    /* a chunk costs ~50 us of its own (kernel ramps, one host round trip for its map), the first upload and
+     * the last download are not overlapped: english1g end to end 27.1 / 25.2 / 23.6 / 23.1 ms with chunks of
+     * 8 / 16 / 32 / 64 MiB (profiles/r02i_host_chunk_sweep.txt) */
+    uint64_t chunk = ctx->pipe_chunk_bytes;
+    if (ctx->pipe_chunk_default && nbytes >= (512ull << 20)) chunk = 64ull << 20;
+    uint64_t cbytes = chunk / tile_bytes * tile_bytes;
     if (cbytes < tile_bytes) cbytes = tile_bytes;
     const int K = (int)((nbytes + cbytes - 1) / cbytes);
     int rc;
