@@ -43,6 +43,7 @@ struct hb_ctx {
     int ep_wf = 0, ep_rshift = -1;   /* EP-/E32-table geometry of the flat / 32-bit emit kernels (0 / -1 = automatic) */
     int fsm_copies = -1;             /* transducer table copies in the sync kernel: log2; -1 = automatic = one (measured: 4 copies
                                       * in one 1024-thread CTA 0.494 ms against 0.438 ms with one copy per CTA and 48 warps per SM) */
+    bool auto_warp_emit = true;      /* HB_EMIT_AUTO picks the warp-autonomous E32 kernel (english1g emit 0.576 ms against 0.622) */
     uint32_t e64_wide = 11;          /* E64 index width for short codes in large streams (set from measurements) */
     uint32_t smem_base = 0x400;      /* shared-window address at which a kernel's dynamic shared memory begins (measured) */
     int phase_timing = HB_PHASES_AUTO;
@@ -245,7 +246,7 @@ extern "C" int hb_ctx_set_phase_timing(hb_ctx *ctx, int mode) {
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
     if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS && path != HB_EMIT_FLAT &&
-                 path != HB_EMIT_WORDS32))
+                 path != HB_EMIT_WORDS32 && path != HB_EMIT_WORDS32W))
         return HB_ERR_ARG;
     ctx->emit_path = path;
     return HB_OK;
@@ -817,7 +818,48 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     /* 32-bit table entries, three symbols per probe, 4 (or 8) copies on disjoint banks, the table
      * at a multiple of its size (hb_emit32_kernel): streams of at least four tiles per SM */
     bool done32 = false;
-    if (WPT >= 2 && (ctx->emit_path == HB_EMIT_WORDS32 ||
+    const bool want32w = ctx->emit_path == HB_EMIT_WORDS32W ||
+                         (ctx->emit_path == HB_EMIT_AUTO && ctx->auto_warp_emit && cb->lut.wf64 == HB_WF_MAX &&
+                          a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount);
+    if (WPT >= 2 && want32w) {
+        /* warp-autonomous variant: one staging slice per warp (32 subsequences' worth of output, 25 % head
+         * room, one thread's overhang), the table in front of the slices */
+        const uint32_t Sbits = 32u * (uint32_t)WPT;
+        const uint32_t max_c = (Sbits + cb->lut.minlen - 1) / cb->lut.minlen;
+        const double avg = cb->implied_avg_len > 1.0 ? cb->implied_avg_len : 1.0;
+        uint32_t winw = (uint32_t)(32.0 * Sbits * 1.25 / avg) + 64u;
+        if (winw > 32u * max_c) winw = 32u * max_c;
+        if (winw < max_c) winw = max_c;
+        winw = (winw + 15u) & ~15u;
+        const uint32_t per_sm = (a.ntiles - tile0) / (uint32_t)ctx->prop.multiProcessorCount;
+        uint32_t wf32 = per_sm >= 32u ? 15u : (per_sm >= 8u ? 14u : 12u);
+        if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
+        if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;
+        const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
+        for (; wf32 >= 9u && !done32; wf32--) {
+            const size_t tab = (size_t)4 << wf32;
+            size_t room = limit > tab ? limit - tab : 0;
+            /* shrink the window (more windows per warp tile) before giving up index bits, but not below
+             * half of the typical output */
+            uint32_t ww = winw;
+            while (ww > winw / 2 && 32u * (size_t)((ww + max_c + 32u + 15u) & ~15u) > room) ww -= 16u;
+            const uint32_t stg = (ww + max_c + 32u + 15u) & ~15u;
+            if (ww < max_c || 32u * (size_t)stg > room) continue;
+            ae.wf = wf32;
+            if ((rc = e32_table(ctx, cb, wf32, &ae.fast))) return rc;
+            const size_t total = tab + 32u * (size_t)stg;
+            const uint64_t units = (uint64_t)(a.ntiles - tile0) * (HB_T / 32);
+            uint64_t g = (units + 31) / 32;
+            if (g > (uint64_t)ctx->prop.multiProcessorCount) g = (uint64_t)ctx->prop.multiProcessorCount;
+            CK(cudaFuncSetAttribute(hb_emit32w_kernel<WPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+            hb_emit32w_kernel<WPT, true><<<(int)g, 1024, total, ctx->stream>>>(
+                ae, 0u, 0u, (uint32_t)tab, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, ww, stg, (uint32_t *)(misc + 36));
+            done32 = true;
+            ctx->last_emit = "hb_emit32w_kernel";
+        }
+    }
+    if (!done32 && WPT >= 2 && (ctx->emit_path == HB_EMIT_WORDS32 ||
                      (ctx->emit_path == HB_EMIT_AUTO && cb->lut.wf64 == HB_WF_MAX &&   /* short codes: four symbols per probe pay (fib4g 1.75 vs 1.85 ms) */
                       a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount))) {
         constexpr uint32_t G = 4;

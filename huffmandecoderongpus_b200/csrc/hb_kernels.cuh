@@ -1195,6 +1195,195 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
 }
 
 /* ------------------------------------------------------------------------- */
+/* Warp-autonomous emit kernel (E32-table): every WARP works through the stream on its own -- 32
+ * consecutive subsequences (a "warp tile", an eighth of a sync tile) at a time, with its own staging
+ * slice and its own TMA bulk store, ordered by __syncwarp only.  hb_emit32_kernel's groups of 256
+ * threads meet at five named barriers per tile and wait there for their slowest warp (13 % of the
+ * warps' time); here nothing waits for another warp.
+ *   output base of a warp tile = the sync tile's base (down-sweep) + the symbols of the tile's
+ *   subsequences in front of it: every lane sums 8 of the tile's 256 records (one 16-byte load),
+ *   a warp scan of those sums gives the prefix at every 8th subsequence, lane 4 q holds warp tile q's.
+ *   The staging slice holds `win` bytes plus one thread's overhang; a warp tile with more output
+ *   goes out in several windows, exactly as in the group kernels. */
+template <int WPT, bool ADD>
+__global__ void __launch_bounds__(1024, 1)
+hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t stage_off,
+                  const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
+                  const uint64_t *__restrict__ result, uint8_t *__restrict__ out, uint64_t out_capacity,
+                  uint32_t win, uint32_t stage_bytes, uint32_t *__restrict__ status) {
+    constexpr int T = HB_T;
+    constexpr uint32_t S = 32u * WPT;
+    constexpr uint32_t WT = T / 32;                         /* warp tiles per sync tile */
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tab_bytes = 4u << (a.wf + rshift);
+    uint32_t *s_fast = smem + tab_off / 4u;
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(smem) + stage_off + warp * stage_bytes;   /* 16-aligned */
+    const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
+    if (!ADD && (tab_saddr & (tab_bytes - 1u))) {
+        if (threadIdx.x == 0) atomicOr(status, HB_ST_LAYOUT);
+        return;
+    }
+    if (rshift == 0u) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.fast);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_fast);
+        for (uint32_t i = threadIdx.x; i < (1u << a.wf) / 4u; i += 1024u) dst[i] = __ldg(src + i);
+    } else {
+        for (uint32_t x = threadIdx.x; x < (1u << a.wf); x += 1024u) {
+            const uint32_t ent = __ldg(a.fast + x);
+            for (uint32_t r = 0; r < (1u << rshift); r++) s_fast[(x << rshift) + r] = ent;
+        }
+    }
+    __syncthreads();
+    hb_tables32 tb;
+    tb.fast = s_fast;
+    tb.sc = 2u + rshift;
+    tb.wf = a.wf;
+    tb.fmask = ((1u << a.wf) - 1u) << tb.sc;
+    tb.lanebase = hb_opaque((ADD ? 0u : tab_saddr) | ((lane & ((1u << rshift) - 1u)) << 2));
+    tb.addbase = hb_opaque(tab_saddr);
+    tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    const uint64_t total_valid = result[0];
+    const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
+
+    /* Warp `warp` of CTA b takes the units b * 32 + warp + k * (32 * gridDim.x): always the same eighth q of
+     * a sync tile (32 * gridDim.x is a multiple of 8), so every address it needs advances by a constant. */
+    const uint32_t nunits = a.ntiles * WT, ustep = gridDim.x * 32u;
+    uint32_t u = blockIdx.x * 32u + warp;
+    const uint32_t q = u % WT;
+    const uint32_t *p_words = a.words + ((uint64_t)u * 32u + lane) * WPT;
+    const uint16_t *p_sub = subs + (uint64_t)u * 32u + lane;
+    const uint4 *p_rec8 = reinterpret_cast<const uint4 *>(subs + (uint64_t)(u / WT) * T) + lane;
+    const uint64_t *p_base = tile_base + u / WT;
+    const uint32_t *const words_end = a.words + a.nwords;
+    const bool vec256 = (reinterpret_cast<uintptr_t>(a.words) & 31u) == 0;
+    const bool cap_ok = total_valid <= out_capacity;        /* then no unit can overrun the output */
+    uint32_t w[WPT + 1];
+    uint16_t sub = 0;
+    uint4 rec8 = make_uint4(0u, 0u, 0u, 0u);
+    uint64_t B = 0;
+    auto fetch = [&]() {
+        if (p_words + WPT + 1 <= words_end) {
+            if (WPT % 8 == 0 && vec256) {
+#pragma unroll
+                for (int v = 0; v < WPT / 8; v++)
+                    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(w[8 * v]), "=r"(w[8 * v + 1]), "=r"(w[8 * v + 2]), "=r"(w[8 * v + 3]),
+                                   "=r"(w[8 * v + 4]), "=r"(w[8 * v + 5]), "=r"(w[8 * v + 6]), "=r"(w[8 * v + 7])
+                                 : "l"(p_words + 8 * v));
+            } else {
+#pragma unroll
+                for (int v = 0; v < WPT / 4; v++) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4 *>(p_words) + v);
+                    w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+                }
+            }
+            w[WPT] = __ldg(p_words + WPT);
+        } else {
+#pragma unroll
+            for (int j = 0; j <= WPT; j++) w[j] = p_words + j < words_end ? __ldg(p_words + j) : 0u;
+        }
+        sub = *p_sub;
+        rec8 = __ldg(p_rec8);
+        B = *p_base;
+    };
+    auto advance = [&]() {
+        u += ustep;
+        p_words += (uint64_t)ustep * 32u * WPT;
+        p_sub += (uint64_t)ustep * 32u;
+        p_rec8 += (uint64_t)(ustep / WT) * (T / 8);
+        p_base += ustep / WT;
+    };
+    if (u < nunits) fetch();
+    while (u < nunits) {
+        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        /* symbols of the sync tile's subsequences in front of this warp tile: the sum over the lanes below
+         * 4 q of their 8 records (REDUX), the offset inside the warp tile by a scan */
+        uint32_t s8 = (rec8.x & 0xffffu) >> 5;
+        s8 += rec8.x >> 21;
+        s8 += (rec8.y & 0xffffu) >> 5;
+        s8 += rec8.y >> 21;
+        s8 += (rec8.z & 0xffffu) >> 5;
+        s8 += rec8.z >> 21;
+        s8 += (rec8.w & 0xffffu) >> 5;
+        s8 += rec8.w >> 21;
+        const uint32_t front = __reduce_add_sync(0xffffffffu, lane < 4u * q ? s8 : 0u);
+        const uint32_t nk = __reduce_add_sync(0xffffffffu, c);
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        const uint32_t o = inc - c;
+        const uint64_t Bt = B + front;
+        /* owned bits of my subsequence: the whole of it unless the stream ends inside this warp tile */
+        uint32_t lim = S;
+        if ((uint64_t)(u + 1u) * (32u * S) > a.bits_own) {
+            const uint64_t sub0 = ((uint64_t)u * 32u + lane) * S;
+            lim = sub0 >= a.bits_own ? 0u : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+        }
+        /* symbols past the shard's valid total (a cut-off last codeword) are not written */
+        uint32_t nvalid = nk;
+        const uint64_t left = total_valid - Bt;             /* wraps when Bt > total_valid */
+        if (Bt >= total_valid) nvalid = 0;
+        else if (left < nk) nvalid = (uint32_t)left;
+        const bool full_out = !cap_ok && Bt + nvalid > out_capacity;
+        if (full_out && lane == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
+        const uint32_t unext = u + ustep;
+
+        uint32_t lo_b = 0;
+        for (uint32_t wb = 0; !full_out && (wb == 0 || wb < nk); wb += win) {
+            const bool mine = c && o >= wb && o - wb < win;
+            const bool last_win = wb + win >= nk;
+            const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + Bt + wb) & 15u);
+            /* the previous bulk store must have read the staging slice */
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            hb_tail tl;
+            tl.k = 0u;
+            if (mine) {
+                const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
+                if (lim != S) hb_emit_clipped32<WPT, ADD>(tb, w, lim, e, c, dst);
+                else tl = hb_emit_words32<WPT, ADD>(tb, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+            }
+            /* the window ends behind its last thread's slice (or with the warp tile) */
+            const uint32_t cross = __ballot_sync(0xffffffffu, mine && o + c - wb >= win && o + c < nk);
+            uint32_t hi_b = __shfl_sync(0xffffffffu, o + c, cross ? (int)hb_ctz(cross) : 0);
+            if (!cross) hi_b = nk;
+            if (last_win && unext < nunits) { advance(); fetch(); }
+            __syncwarp();
+            hb_store_tail(tl);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (hi_b > nvalid) hi_b = nvalid;
+            if (lo_b < hi_b) {
+                uint8_t *gbase = out + Bt + wb - al;          /* 16-byte aligned */
+                const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                const uint32_t a0 = (begb + 15u) & ~15u, a1 = endb & ~15u;
+                if (a0 < a1) {
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(gbase + a0), "r"(s_out_saddr + a0), "r"(a1 - a0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (begb + lane < a0) gbase[begb + lane] = s_out[begb + lane];
+                    if (a1 + lane < endb) gbase[a1 + lane] = s_out[a1 + lane];
+                } else {
+                    if (begb + lane < endb) gbase[begb + lane] = s_out[begb + lane];   /* < 32 bytes */
+                }
+            }
+            lo_b = hi_b > lo_b ? hi_b : lo_b;
+        }
+        if (u != unext) {                        /* not advanced inside the window loop */
+            advance();
+            if (u < nunits) fetch();
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------------- */
 /* Emit kernel, flat variant (hb_emit_flat in hb_core.cuh): full tiles that are not the last
  * tile of the shard.  A CTA is G groups of HB_T threads, each on its own tile behind its own
  * named barrier, sharing ONE EP-table built in shared memory by the CTA itself (R copies,

@@ -110,6 +110,8 @@ int  hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies);
                              slower than HB_EMIT_WORDS, never chosen by HB_EMIT_AUTO */
 #define HB_EMIT_WORDS32 4 /* hb_emit32_kernel: word stores, 32-bit table entries with up to three symbols, 4
                              (or 8) copies of the table on disjoint banks */
+#define HB_EMIT_WORDS32W 5 /* hb_emit32w_kernel: the same probes, every warp on its own (own staging slice, own bulk
+                             store, no block-level barriers) */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
 /* name of the emit kernel the last decode used for the bulk of its tiles ("" before the first) */
 const char *hb_ctx_last_emit_kernel(const hb_ctx *ctx);

@@ -429,6 +429,69 @@ struct Emul {
         return true;
     }
 
+    /* mirrors hb_emit32w_kernel, one tile: every group of 32 subsequences (a warp) on its own, with its
+     * own output base (tile base + the symbols in front of it), windows and copy-out */
+    bool emit_tile_warp(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
+                        uint64_t total_valid) {
+        const uint64_t tile_bit0 = (uint64_t)tile * TS;
+        constexpr int L = T >= 32 ? 32 : T;             /* lanes per warp tile */
+        uint32_t front = 0;
+        for (int q = 0; q < T / L; q++) {
+            const int t0 = q * L;
+            const uint64_t B = tile_base[tile] + front;
+            uint32_t o_acc = 0;
+            std::vector<uint32_t> off(L), cnt(L);
+            for (int l = 0; l < L; l++) { off[l] = o_acc; cnt[l] = hb_sub_count(subs[(uint64_t)tile * T + t0 + l]); o_acc += cnt[l]; }
+            const uint32_t nk = o_acc;
+            front += nk;
+            uint32_t nvalid = nk;
+            if (B >= total_valid) nvalid = 0;
+            else if (B + nk > total_valid) nvalid = (uint32_t)(total_valid - B);
+            if (B + nvalid > out_capacity) return false;
+            uint32_t lo_b = 0;
+            for (uint32_t wb = 0; wb == 0 || wb < nk; wb += win) {
+                std::vector<uint8_t> s_out(stage_bytes + 64, 0xEE);
+                const uint32_t al = (uint32_t)((reinterpret_cast<uintptr_t>(out) + B + wb) & 15u);
+                uint32_t hi_b = nk;
+                std::vector<hb_tail> tails;
+                for (int l = 0; l < L; l++) {
+                    const int t = t0 + l;
+                    const uint32_t o = off[l], c = cnt[l];
+                    const bool mine = c && o >= wb && o - wb < win;
+                    if (!mine) continue;
+                    const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
+                    const uint32_t lim = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
+                    const uint32_t e = hb_sub_entry(subs[(uint64_t)tile * T + t]);
+                    if (al + (o - wb) + c > stage_bytes) return false;      /* staging bound violated */
+                    uint32_t w[WPT + 1];
+                    load((uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+                    uint8_t *dst = s_out.data() + al + (o - wb);
+                    const uint8_t canary = dst[c];
+                    const uint32_t mis = (al + (o - wb)) & 3u;
+                    uint32_t n = c;
+                    if (lim != S || WPT < 2) n = hb_emit_clipped32<WPT>(tbE32, w, lim, e, c, dst);
+                    else if constexpr (WPT >= 2) {
+                        tails.push_back(hb_emit_words32<WPT>(tbE32, w, e, c, dst, mis));
+                        if ((uint32_t)((tails.back().at + tails.back().k) - dst) != c) return false;
+                    }
+                    if (n != c) return false;
+                    if (dst[c] != canary) return false;
+                    st.probes_emit += n;
+                    if (o + c - wb >= win && o + c < nk) hi_b = o + c;
+                }
+                for (const hb_tail &tl : tails) hb_store_tail(tl);
+                if (hi_b > nvalid) hi_b = nvalid;
+                if (lo_b < hi_b) {
+                    uint8_t *gbase = out + B + wb - al;
+                    const uint32_t begb = al + (lo_b - wb), endb = al + (hi_b - wb);
+                    for (uint32_t i = begb; i < endb; i++) gbase[i] = s_out[i];
+                }
+                lo_b = hi_b > lo_b ? hi_b : lo_b;
+            }
+        }
+        return true;
+    }
+
     /* mirrors hb_emit_kernel, one tile; returns false on output overflow */
     bool emit_tile(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
                    uint64_t total_valid) {
@@ -525,7 +588,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow, 3u, 0u};
-    if (emit_mode == 3) {   /* E32-table exactly as hb_emit32_kernel builds it (index width: ep_wf, else wf64) */
+    if (emit_mode == 3 || emit_mode == 4) {   /* E32-table exactly as hb_emit32_kernel builds it (index width: ep_wf, else wf64) */
         uint32_t wf32 = ep_wf ? ep_wf : wf64;
         if (wf32 > maxlen && maxlen >= 9u) wf32 = maxlen;
         E.e32tab.resize((size_t)1 << wf32);
@@ -559,6 +622,13 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
         }
         for (uint32_t tile = 0; tile < E.ntiles; tile++) {
             const bool flat = E.flat && tile + 1 < E.ntiles;
+            if (emit_mode == 4) {    /* warp tiles: a window sized for 32 subsequences */
+                const uint32_t L = T >= 32 ? 32u : (uint32_t)T;
+                uint32_t ww = emit_win ? emit_win : ((L * max_c + 15u) & ~15u);
+                if (ww < ((max_c + 15u) & ~15u)) ww = (max_c + 15u) & ~15u;
+                if (!E.emit_tile_warp(tile, out, out_capacity, ww, (ww + max_c + 32u + 15u) & ~15u, res[0])) { rc = -6; break; }
+                continue;
+            }
             if (flat ? !E.emit_tile_flat(tile, out, out_capacity, win, stage + 16)
                      : !E.emit_tile(tile, out, out_capacity, win, stage, res[0])) { rc = -6; break; }
         }

@@ -75,7 +75,8 @@ def run(lut, words, bits_own, bits_avail, wpt=4, T=256, entry=0, base=0, emit=Tr
     product's default dispatch), 2 = both, failing (rc -101) unless they agree.
     emit_mode: 0 = byte-store emit walk, 1 = word-store walk (WPT >= 2; narrower test
     shapes fall back to bytes), 2 = flat walk (EP-table of ep_wf index bits) on every tile
-    but the last one (wpt >= 4), word-store walk on the last."""
+    but the last one (wpt >= 4), word-store walk on the last, 3 = word-store walk with the E32-table
+    (index width ep_wf, 0 = the E64 default), 4 = the same per warp tile of 32 subsequences."""
     cap = int(out_capacity if out_capacity is not None else bits_own + 64)
     raw = np.zeros(cap + 64 + out_offset, dtype=np.uint8)
     out = raw[out_offset:]

@@ -394,7 +394,7 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0"):
+    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0", "words32w", "words32w:12:0", "words32w:15:0"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         if ":" in path:     # E32-table geometry: index bits, log2(copies)
             _, wf, rs = path.split(":")
