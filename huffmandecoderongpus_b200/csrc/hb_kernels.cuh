@@ -1317,19 +1317,19 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
         }
         const uint32_t o = inc - c;
         const uint64_t Bt = B + front;
-        /* owned bits of my subsequence: the whole of it unless the stream ends inside this warp tile */
-        uint32_t lim = S;
-        if ((uint64_t)(u + 1u) * (32u * S) > a.bits_own) {
+        /* Only in the shard's last sync tile can the stream end inside a subsequence, or the shard's last
+         * codeword be cut off (its symbol is then not part of total_valid): everywhere else every
+         * subsequence is whole and every symbol valid, and the 64-bit bookkeeping is skipped. */
+        uint32_t lim = S, nvalid = nk;
+        bool full_out = false;
+        if (u + WT >= nunits || !cap_ok) {
             const uint64_t sub0 = ((uint64_t)u * 32u + lane) * S;
             lim = sub0 >= a.bits_own ? 0u : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+            if (Bt >= total_valid) nvalid = 0;
+            else if (total_valid - Bt < nk) nvalid = (uint32_t)(total_valid - Bt);
+            full_out = Bt + nvalid > out_capacity;
+            if (full_out && lane == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
         }
-        /* symbols past the shard's valid total (a cut-off last codeword) are not written */
-        uint32_t nvalid = nk;
-        const uint64_t left = total_valid - Bt;             /* wraps when Bt > total_valid */
-        if (Bt >= total_valid) nvalid = 0;
-        else if (left < nk) nvalid = (uint32_t)left;
-        const bool full_out = !cap_ok && Bt + nvalid > out_capacity;
-        if (full_out && lane == 0) atomicOr(status, HB_ST_OUTPUT_FULL);
         const uint32_t unext = u + ustep;
 
         uint32_t lo_b = 0;
