@@ -239,8 +239,42 @@ def test_output_too_small_and_bad_args(ctx, dev):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("name,nshards", [("paper1", 3), ("kjv", 2), ("kjv", 8), ("ecoli", 4)])
-def test_byte_range_shards_on_one_gpu(dev, name, nshards):
+@pytest.mark.parametrize("path", ["words32w", "words32", "words"])
+def test_word_store_kernels_edge_cases(dev, path):
+    """The word-store emit kernels on the cases that exercise their end-of-stream bookkeeping (forced
+    here: the automatic choice uses them for large streams only): streams cut inside a codeword and at
+    every position around word / subsequence / tile boundaries, every output alignment with nothing
+    written outside the slice, an output buffer that is too small or exactly large enough."""
+    f = _stream("paper1")
+    st = O.Stream(f.tree, f.data, f.bits, f.usize)
+    c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    c.set_emit_path(path)
+    cb = hb.Codebook(c, f.tree)
+    for bits in [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 65535, 65536, 65537, 100001, f.bits - 1]:
+        want = O.simple_decode(st, bits=bits)
+        got, res, _ = _decode_dev(c, cb, f, dev, bits=bits, cap=want.size + 8)
+        assert res["n_symbols"] == want.size and np.array_equal(got, want), bits
+    want = O.simple_decode(st)
+    for off in (0, 1, 3, 7, 8, 15):
+        got, res, raw = _decode_dev(c, cb, f, dev, out_offset=off)
+        host = raw.cpu().numpy()
+        assert np.array_equal(got, want) and not host[:off].any() and not host[off + want.size:].any()
+    got, res, _ = _decode_dev(c, cb, f, dev, cap=f.usize)            # exactly large enough
+    assert res["n_symbols"] == f.usize and np.array_equal(got, want)
+    for short in (1, 17, 5000):
+        with pytest.raises(hb.HuffError) as e:
+            _decode_dev(c, cb, f, dev, cap=f.usize - short)
+        assert e.value.code == -6
+    got, res, _ = _decode_dev(c, cb, f, dev)                         # the context still works afterwards
+    assert np.array_equal(got, want)
+    cb.close()
+    c.close()
+
+
+@pytest.mark.parametrize("name,nshards,path", [("paper1", 3, "auto"), ("kjv", 2, "auto"), ("kjv", 8, "auto"),
+                                               ("ecoli", 4, "auto"), ("kjv", 3, "words32w"), ("paper1", 2, "words32w"),
+                                               ("kjv", 2, "words32")])
+def test_byte_range_shards_on_one_gpu(dev, name, nshards, path):
     """The multi-GPU decomposition with every 'rank' run on cuda:0: one context
     per rank, maps gathered by concatenation, hb_shard_compose, independent emit."""
     f = _stream(name)
@@ -249,6 +283,8 @@ def test_byte_range_shards_on_one_gpu(dev, name, nshards):
     bounds = [r * per for r in range(nshards)] + [f.nbytes]
     stream = torch.cuda.current_stream().cuda_stream
     ctxs = [hb.Context(0, stream=stream) for _ in range(nshards)]
+    for c in ctxs:
+        c.set_emit_path(path)
     cbs = [hb.Codebook(c, f.tree) for c in ctxs]
     all_maps = torch.zeros(nshards * 32, dtype=torch.int64, device=dev)
     shards = []

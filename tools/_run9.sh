@@ -1,14 +1,2 @@
-O=gpurun_out/r03p; mkdir -p $O
-HB_STRESS_SEEDS=10 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -4 $O/pytest.log
-B="python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-secondary"
-for v in "--emit-path words32w" ; do
-  echo "== english1g $v" >> $O/ab.log; $B $v >> $O/ab.log 2>&1
-done
-python - <<'PY'
-import json
-for l in open('gpurun_out/r03p/ab.log'):
-    if l.startswith('=='): print(l.strip()); continue
-    if l.startswith('{'):
-        d=json.loads(l); print('   ms/step %.4f  GB/s %.1f launches %s kernels %s' % (d['ms_per_step'], d['value'], d['gpu_launches'], d['roofline']['kernel_ms']))
-    else: print('   '+l.strip()[:200])
-PY
+O=gpurun_out/r03s; mkdir -p $O
+HB_STRESS_SEEDS=30 HB_STRESS_CASES=16 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -4 $O/pytest.log
