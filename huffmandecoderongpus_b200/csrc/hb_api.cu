@@ -819,7 +819,7 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
      * at a multiple of its size (hb_emit32_kernel): streams of at least four tiles per SM */
     bool done32 = false;
     const bool want32w = ctx->emit_path == HB_EMIT_WORDS32W ||
-                         (ctx->emit_path == HB_EMIT_AUTO && ctx->auto_warp_emit && cb->lut.wf64 == HB_WF_MAX &&
+                         (ctx->emit_path == HB_EMIT_AUTO && ctx->auto_warp_emit &&
                           a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount);
     if (WPT >= 2 && want32w) {
         /* warp-autonomous variant: one staging slice per warp (32 subsequences' worth of output, 25 % head
@@ -836,15 +836,21 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
         if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
         if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;
         const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
-        for (; wf32 >= 9u && !done32; wf32--) {
-            const size_t tab = (size_t)4 << wf32;
+        /* the widest table beside which the whole window still fits (a second window per warp tile costs far
+         * more than an index bit: fib4g 2.74 ms with 15 bits and two windows, 1.69 ms with 14 and one); on
+         * request (HB_EMIT_WORDS32W) a smaller window with the narrowest table rather than no launch */
+        const uint32_t wf_min = ctx->emit_path == HB_EMIT_WORDS32W ? 9u : 12u;
+        for (int pass = 0; pass < 2 && !done32; pass++)
+        for (uint32_t wfx = wf32; wfx >= wf_min && !done32; wfx--) {
+            const size_t tab = (size_t)4 << wfx;
             size_t room = limit > tab ? limit - tab : 0;
-            /* shrink the window (more windows per warp tile) before giving up index bits, but not below
-             * half of the typical output */
             uint32_t ww = winw;
-            while (ww > winw / 2 && 32u * (size_t)((ww + max_c + 32u + 15u) & ~15u) > room) ww -= 16u;
+            if (pass == 1)      /* second pass: shrink the window, never below one thread's output */
+                while (ww > max_c + 16u && 32u * (size_t)((ww + max_c + 32u + 15u) & ~15u) > room) ww -= 16u;
             const uint32_t stg = (ww + max_c + 32u + 15u) & ~15u;
             if (ww < max_c || 32u * (size_t)stg > room) continue;
+            if (pass == 1 && ctx->emit_path != HB_EMIT_WORDS32W) break;   /* automatic: the group kernels instead */
+            const uint32_t wf32 = wfx;
             ae.wf = wf32;
             if ((rc = e32_table(ctx, cb, wf32, &ae.fast))) return rc;
             const size_t total = tab + 32u * (size_t)stg;
