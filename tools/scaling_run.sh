@@ -1,0 +1,11 @@
+# usage: bash tools/scaling_run.sh N   (on a box with N GPUs)
+n=$1; O=gpurun_out/r02k; mkdir -p $O
+nvidia-smi -L | wc -l
+(time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 30 --warmup 3) > $O/bench_n$n.log 2>&1; echo "rc $?" >> $O/bench_n$n.log
+grep '^{' $O/bench_n$n.log | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print('N',d['n_gpus'],'value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',d['e2e'] and round(d['e2e']['value'],1), {k:(round(v['value'],1),round(v['ms_per_step'],4)) for k,v in d['secondary'].items() if 'value' in v})
+"
+cd huffmandecoderongpus_b200/host
+(B200_DEVICES=$n timeout 600 ./HuffFramework synth1g; B200_DEVICES=$n timeout 600 ./HuffFramework synth16g) > ../../$O/harness_synth_$n.log 2>&1; grep "b200" ../../$O/harness_synth_$n.log
