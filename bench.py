@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--ep-copies-log2", type=int, default=-1, help="log2 of the EP-table copies (-1 = auto)")
     ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat", "words32", "words32w"],
                     help="emit kernel A/B (auto = words)")
+    ap.add_argument("--emit-spl", type=int, default=1, choices=[1, 2], help="subsequences per lane of the warp-autonomous emit kernel")
     ap.add_argument("--sync-copies-log2", type=int, default=-1, help="transducer table copies in the sync kernel (log2; -1 = auto)")
     ap.add_argument("--sync-path", default="auto", choices=["auto", "probe", "fsm"],
                     help="sync kernel A/B")
@@ -376,6 +377,7 @@ def main():
                      words_per_thread=args.wpt, ctas_per_sm=args.ctas_per_sm)
     ctx.set_sync_path(args.sync_path)
     ctx.set_sync_copies(args.sync_copies_log2)
+    ctx.set_emit_lane_subsequences(args.emit_spl)
     if args.host_chunk_mib:
         ctx.set_host_chunk(args.host_chunk_mib << 20)
     ctx.set_emit_path(args.emit_path)

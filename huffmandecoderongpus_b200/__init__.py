@@ -115,6 +115,7 @@ def lib():
     L.hb_ctx_set_phase_timing.argtypes = [vp, i32]
     L.hb_codebook_download_table.argtypes = [vp, i32, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.hb_ctx_set_sync_copies.argtypes = [vp, i32]
+    L.hb_ctx_set_emit_lane_subsequences.argtypes = [vp, i32]
     L.hb_ctx_last_emit_kernel.argtypes = [vp]
     L.hb_ctx_last_emit_kernel.restype = C.c_char_p
     L.hb_ctx_set_emit_path.argtypes = [vp, i32]
@@ -309,6 +310,10 @@ class Context:
         """"auto", "always" or "never": whether decodes record the per-phase events."""
         _check(lib().hb_ctx_set_phase_timing(self.h, {"auto": 0, "always": 1, "never": 2}[mode]),
                "hb_ctx_set_phase_timing")
+
+    def set_emit_lane_subsequences(self, n=1):
+        """hb_emit32w_kernel: consecutive subsequences per lane (1 or 2)"""
+        _check(lib().hb_ctx_set_emit_lane_subsequences(self.h, n), "hb_ctx_set_emit_lane_subsequences")
 
     def last_emit_kernel(self):
         """name of the emit kernel the last decode used for the bulk of its tiles"""

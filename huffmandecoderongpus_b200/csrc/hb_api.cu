@@ -43,6 +43,10 @@ struct hb_ctx {
     int ep_wf = 0, ep_rshift = -1;   /* EP-/E32-table geometry of the flat / 32-bit emit kernels (0 / -1 = automatic) */
     int fsm_copies = -1;             /* transducer table copies in the sync kernel: log2; -1 = automatic = one (measured: 4 copies
                                       * in one 1024-thread CTA 0.494 ms against 0.438 ms with one copy per CTA and 48 warps per SM) */
+    int warp_spl = 1;                /* subsequences per lane of the warp-autonomous emit kernel: 2 halves the per-warp-tile
+                                      * work per stream bit but was measured slower (english1g emit 0.628 against 0.558 ms: the
+                                      * second subsequence's words are loaded in the middle of the chain, and the doubled
+                                      * staging slices leave room for a 14-bit table only) */
     bool auto_warp_emit = true;      /* HB_EMIT_AUTO picks the warp-autonomous E32 kernel (english1g emit 0.576 ms against 0.622) */
     uint32_t e64_wide = 11;          /* E64 index width for short codes in large streams (set from measurements) */
     uint32_t smem_base = 0x400;      /* shared-window address at which a kernel's dynamic shared memory begins (measured) */
@@ -231,6 +235,12 @@ extern "C" int hb_ctx_set_sync_path(hb_ctx *ctx, int path) {
 }
 
 extern "C" const char *hb_ctx_last_emit_kernel(const hb_ctx *ctx) { return ctx ? ctx->last_emit : ""; }
+
+extern "C" int hb_ctx_set_emit_lane_subsequences(hb_ctx *ctx, int n) {
+    if (!ctx || (n != 1 && n != 2)) return HB_ERR_ARG;
+    ctx->warp_spl = n;
+    return HB_OK;
+}
 
 extern "C" int hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies) {
     if (!ctx || log2_copies < -1 || log2_copies > 2) return HB_ERR_ARG;
@@ -824,45 +834,55 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     if (WPT >= 2 && want32w) {
         /* warp-autonomous variant: one staging slice per warp (32 subsequences' worth of output, 25 % head
          * room, one thread's overhang), the table in front of the slices */
-        const uint32_t Sbits = 32u * (uint32_t)WPT;
-        const uint32_t max_c = (Sbits + cb->lut.minlen - 1) / cb->lut.minlen;
-        const double avg = cb->implied_avg_len > 1.0 ? cb->implied_avg_len : 1.0;
-        uint32_t winw = (uint32_t)(32.0 * Sbits * 1.25 / avg) + 64u;
-        if (winw > 32u * max_c) winw = 32u * max_c;
-        if (winw < max_c) winw = max_c;
-        winw = (winw + 15u) & ~15u;
-        const uint32_t per_sm = (a.ntiles - tile0) / (uint32_t)ctx->prop.multiProcessorCount;
-        uint32_t wf32 = per_sm >= 32u ? 15u : (per_sm >= 8u ? 14u : 12u);
-        if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf32 = (uint32_t)ctx->ep_wf;
-        if (wf32 > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf32 = cb->lut.maxlen;
         const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
-        /* the widest table beside which the whole window still fits (a second window per warp tile costs far
-         * more than an index bit: fib4g 2.74 ms with 15 bits and two windows, 1.69 ms with 14 and one); on
-         * request (HB_EMIT_WORDS32W) a smaller window with the narrowest table rather than no launch */
+        const uint32_t per_sm = (a.ntiles - tile0) / (uint32_t)ctx->prop.multiProcessorCount;
+        uint32_t wf_want = per_sm >= 32u ? 15u : (per_sm >= 8u ? 14u : 12u);
+        if (ctx->ep_wf >= 9 && ctx->ep_wf <= HB_E32_WF_MAX) wf_want = (uint32_t)ctx->ep_wf;
+        if (wf_want > cb->lut.maxlen && cb->lut.maxlen >= 9u) wf_want = cb->lut.maxlen;
         const uint32_t wf_min = ctx->emit_path == HB_EMIT_WORDS32W ? 9u : 12u;
-        for (int pass = 0; pass < 2 && !done32; pass++)
-        for (uint32_t wfx = wf32; wfx >= wf_min && !done32; wfx--) {
-            const size_t tab = (size_t)4 << wfx;
-            size_t room = limit > tab ? limit - tab : 0;
-            uint32_t ww = winw;
-            if (pass == 1)      /* second pass: shrink the window, never below one thread's output */
-                while (ww > max_c + 16u && 32u * (size_t)((ww + max_c + 32u + 15u) & ~15u) > room) ww -= 16u;
-            const uint32_t stg = (ww + max_c + 32u + 15u) & ~15u;
-            if (ww < max_c || 32u * (size_t)stg > room) continue;
-            if (pass == 1 && ctx->emit_path != HB_EMIT_WORDS32W) break;   /* automatic: the group kernels instead */
-            const uint32_t wf32 = wfx;
-            ae.wf = wf32;
-            if ((rc = e32_table(ctx, cb, wf32, &ae.fast))) return rc;
-            const size_t total = tab + 32u * (size_t)stg;
-            const uint64_t units = (uint64_t)(a.ntiles - tile0) * (HB_T / 32);
-            uint64_t g = (units + 31) / 32;
-            if (g > (uint64_t)ctx->prop.multiProcessorCount) g = (uint64_t)ctx->prop.multiProcessorCount;
-            CK(cudaFuncSetAttribute(hb_emit32w_kernel<WPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-            hb_emit32w_kernel<WPT, true><<<(int)g, 1024, total, ctx->stream>>>(
-                ae, 0u, 0u, (uint32_t)tab, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
-                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, ww, stg, (uint32_t *)(misc + 36));
-            done32 = true;
-            ctx->last_emit = "hb_emit32w_kernel";
+        /* ctx->warp_spl subsequences per lane (A/B knob), else one.  For each: the widest table beside which
+         * the whole window still fits (a second window per warp tile costs far more than an index bit: fib4g
+         * 2.74 ms with 15 bits and two windows, 1.69 ms with 14 and one); on request (HB_EMIT_WORDS32W) a
+         * smaller window with the narrowest table rather than no launch. */
+        for (uint32_t spl = (uint32_t)ctx->warp_spl; spl >= 1u && !done32; spl--) {
+            const uint32_t Sbits = 32u * (uint32_t)WPT * spl;      /* stream bits per lane */
+            const uint32_t max_c = (Sbits + cb->lut.minlen - 1) / cb->lut.minlen;
+            const double avg = cb->implied_avg_len > 1.0 ? cb->implied_avg_len : 1.0;
+            uint32_t winw = (uint32_t)(32.0 * Sbits * 1.25 / avg) + 64u;
+            if (winw > 32u * max_c) winw = 32u * max_c;
+            if (winw < max_c) winw = max_c;
+            winw = (winw + 15u) & ~15u;
+            for (int pass = 0; pass < 2 && !done32; pass++)
+            for (uint32_t wfx = wf_want; wfx >= wf_min && !done32; wfx--) {
+                const size_t tab = (size_t)4 << wfx;
+                size_t room = limit > tab ? limit - tab : 0;
+                uint32_t ww = winw;
+                if (pass == 1)      /* second pass: shrink the window, never below one thread's output */
+                    while (ww > max_c + 16u && 32u * (size_t)((ww + max_c + 32u + 15u) & ~15u) > room) ww -= 16u;
+                const uint32_t stg = (ww + max_c + 32u + 15u) & ~15u;
+                if (ww < max_c || 32u * (size_t)stg > room) continue;
+                if (pass == 1 && (ctx->emit_path != HB_EMIT_WORDS32W || spl > 1u)) break;   /* rather one subsequence per lane / the group kernels */
+                ae.wf = wfx;
+                if ((rc = e32_table(ctx, cb, wfx, &ae.fast))) return rc;
+                const size_t total = tab + 32u * (size_t)stg;
+                const uint64_t units = (uint64_t)(a.ntiles - tile0) * (HB_T / (32u * spl));
+                uint64_t g = (units + 31) / 32;
+                if (g > (uint64_t)ctx->prop.multiProcessorCount) g = (uint64_t)ctx->prop.multiProcessorCount;
+#define HB_LAUNCH_EMIT32W(SPL)                                                                                      \
+                do {                                                                                                \
+                    CK(cudaFuncSetAttribute(hb_emit32w_kernel<WPT, true, SPL>,                                      \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));              \
+                    hb_emit32w_kernel<WPT, true, SPL><<<(int)g, 1024, total, ctx->stream>>>(                        \
+                        ae, 0u, 0u, (uint32_t)tab, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p, \
+                        (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, ww, stg,                     \
+                        (uint32_t *)(misc + 36));                                                                   \
+                } while (0)
+                if (spl == 2u) HB_LAUNCH_EMIT32W(2);
+                else HB_LAUNCH_EMIT32W(1);
+#undef HB_LAUNCH_EMIT32W
+                done32 = true;
+                ctx->last_emit = "hb_emit32w_kernel";
+            }
         }
     }
     if (!done32 && WPT >= 2 && (ctx->emit_path == HB_EMIT_WORDS32 ||

@@ -668,12 +668,22 @@ HB_HD uint32_t hb_push32(uint32_t ent, uint32_t t, uint32_t &pend, uint32_t posk
     return posk_n;
 }
 
+/* A chain may be walked in parts of WPT words each (hb_emit32w_kernel's lanes take two consecutive
+ * subsequences: their output is contiguous and the chain simply runs on): st carries the position, the
+ * register window and the staging pointer from part to part.  `last`: this part ends the lane's chain --
+ * only then are the final probes clipped to the count c (of the WHOLE chain). */
+struct hb_w32 { uint32_t acc, pend, posk; hb_out_t wpp; };
+
+HB_HD void hb_w32_begin(hb_w32 &st, uint32_t e, hb_out_t out, uint32_t mis) {
+    st.acc = e; st.pend = 0u; st.posk = 8u * mis; st.wpp = out - mis;
+}
+
 template <int WPT, bool ADD = false>
-HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
-                              uint32_t c, hb_out_t out, uint32_t mis) {
+HB_HD void hb_emit_words32_part(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], hb_w32 &st,
+                                uint32_t c, hb_out_t out, bool last) {
     const uint32_t SC = tb.sc;
-    uint32_t acc = e, pend = 0u, posk = 8u * mis;
-    hb_out_t wpp = out - mis;
+    uint32_t acc = st.acc, pend = st.pend, posk = st.posk;
+    hb_out_t wpp = st.wpp;
 #pragma unroll
     for (int j = 0; j < WPT - 1; j++) {
         const uint32_t lo = w[j], hi = w[j + 1];
@@ -699,7 +709,7 @@ HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1
          * subsequence; their symbols are clipped to the chain's count c. */
         const uint32_t lo = w[WPT - 1], hi = w[WPT];
         const uint32_t los = hb_keep(lo << SC), his = hb_funnel_l(lo, hi, SC);
-        const uint32_t safe = 32u - tb.wf;
+        const uint32_t safe = last ? 32u - tb.wf : 31u;   /* not the last part: no probe is clipped */
         bool done = false;
         for (;;) {
             if (acc <= safe) {
@@ -738,11 +748,25 @@ HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1
             }
         }
     }
+    if (!last) acc -= 32u;
+    st.acc = acc; st.pend = pend; st.posk = posk; st.wpp = wpp;
+}
+
+HB_HD hb_tail hb_w32_tail(const hb_w32 &st) {
     hb_tail tl;
-    tl.k = (posk >> 3) & 3u;
-    tl.bytes = tl.k ? pend >> ((32u - 8u * tl.k) & 31u) : 0u;
-    tl.at = wpp;
+    tl.k = (st.posk >> 3) & 3u;
+    tl.bytes = tl.k ? st.pend >> ((32u - 8u * tl.k) & 31u) : 0u;
+    tl.at = st.wpp;
     return tl;
+}
+
+template <int WPT, bool ADD = false>
+HB_HD hb_tail hb_emit_words32(const hb_tables32 &tb, const uint32_t (&w)[WPT + 1], uint32_t e,
+                              uint32_t c, hb_out_t out, uint32_t mis) {
+    hb_w32 st;
+    hb_w32_begin(st, e, out, mis);
+    hb_emit_words32_part<WPT, ADD>(tb, w, st, c, out, true);
+    return hb_w32_tail(st);
 }
 
 /* Partial subsequence (stream tail): byte stores, every symbol clipped to the chain's count c */

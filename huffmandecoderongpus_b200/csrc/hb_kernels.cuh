@@ -1205,7 +1205,12 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
  *   a warp scan of those sums gives the prefix at every 8th subsequence, lane 4 q holds warp tile q's.
  *   The staging slice holds `win` bytes plus one thread's overhang; a warp tile with more output
  *   goes out in several windows, exactly as in the group kernels. */
-template <int WPT, bool ADD>
+/* SPL = 2: a lane takes TWO consecutive subsequences (a warp tile is 64 of them, a quarter of a sync tile):
+ * their output is contiguous and the chain runs on from one into the other (hb_emit_words32_part), so the
+ * per-warp-tile prologue and epilogue -- 40 % of the kernel's instructions with SPL = 1 -- are paid once per
+ * 512 stream bits instead of once per 256.  The second subsequence's words are loaded when the first is done.
+ * Byte-exact, but measured slower than SPL = 1 (english1g 0.628 against 0.558 ms): an A/B path. */
+template <int WPT, bool ADD, int SPL>
 __global__ void __launch_bounds__(1024, 1)
 hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t stage_off,
                   const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
@@ -1213,7 +1218,8 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
                   uint32_t win, uint32_t stage_bytes, uint32_t *__restrict__ status) {
     constexpr int T = HB_T;
     constexpr uint32_t S = 32u * WPT;
-    constexpr uint32_t WT = T / 32;                         /* warp tiles per sync tile */
+    constexpr uint32_t UNIT = 32u * SPL;                    /* subsequences per warp tile */
+    constexpr uint32_t WT = T / UNIT;                       /* warp tiles per sync tile */
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tab_bytes = 4u << (a.wf + rshift);
@@ -1251,18 +1257,18 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
     const uint32_t nunits = a.ntiles * WT, ustep = gridDim.x * 32u;
     uint32_t u = blockIdx.x * 32u + warp;
     const uint32_t q = u % WT;
-    const uint32_t *p_words = a.words + ((uint64_t)u * 32u + lane) * WPT;
-    const uint16_t *p_sub = subs + (uint64_t)u * 32u + lane;
+    const uint32_t *p_words = a.words + ((uint64_t)u * UNIT + lane * SPL) * WPT;
+    const uint16_t *p_sub = subs + (uint64_t)u * UNIT + lane * SPL;
     const uint4 *p_rec8 = reinterpret_cast<const uint4 *>(subs + (uint64_t)(u / WT) * T) + lane;
     const uint64_t *p_base = tile_base + u / WT;
     const uint32_t *const words_end = a.words + a.nwords;
     const bool vec256 = (reinterpret_cast<uintptr_t>(a.words) & 31u) == 0;
     const bool cap_ok = total_valid <= out_capacity;        /* then no unit can overrun the output */
     uint32_t w[WPT + 1];
-    uint16_t sub = 0;
+    uint32_t sub = 0;                                       /* my record(s): the second one in the high half */
     uint4 rec8 = make_uint4(0u, 0u, 0u, 0u);
     uint64_t B = 0;
-    auto fetch = [&]() {
+    auto load_words = [&](const uint32_t *p_words) {
         if (p_words + WPT + 1 <= words_end) {
             if (WPT % 8 == 0 && vec256) {
 #pragma unroll
@@ -1283,20 +1289,24 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
 #pragma unroll
             for (int j = 0; j <= WPT; j++) w[j] = p_words + j < words_end ? __ldg(p_words + j) : 0u;
         }
-        sub = *p_sub;
+    };
+    auto fetch = [&]() {
+        load_words(p_words);
+        sub = SPL == 2 ? *reinterpret_cast<const uint32_t *>(p_sub) : (uint32_t)*p_sub;
         rec8 = __ldg(p_rec8);
         B = *p_base;
     };
     auto advance = [&]() {
         u += ustep;
-        p_words += (uint64_t)ustep * 32u * WPT;
-        p_sub += (uint64_t)ustep * 32u;
+        p_words += (uint64_t)ustep * UNIT * WPT;
+        p_sub += (uint64_t)ustep * UNIT;
         p_rec8 += (uint64_t)(ustep / WT) * (T / 8);
         p_base += ustep / WT;
     };
     if (u < nunits) fetch();
     while (u < nunits) {
-        const uint32_t e = hb_sub_entry(sub), c = hb_sub_count(sub);
+        const uint32_t e = hb_sub_entry((uint16_t)sub), c0 = hb_sub_count((uint16_t)sub);
+        const uint32_t c = c0 + (SPL == 2 ? sub >> 21 : 0u);
         /* symbols of the sync tile's subsequences in front of this warp tile: the sum over the lanes below
          * 4 q of their 8 records (REDUX), the offset inside the warp tile by a scan */
         uint32_t s8 = (rec8.x & 0xffffu) >> 5;
@@ -1307,7 +1317,7 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
         s8 += rec8.z >> 21;
         s8 += (rec8.w & 0xffffu) >> 5;
         s8 += rec8.w >> 21;
-        const uint32_t front = __reduce_add_sync(0xffffffffu, lane < 4u * q ? s8 : 0u);
+        const uint32_t front = __reduce_add_sync(0xffffffffu, lane < (UNIT / 8u) * q ? s8 : 0u);
         const uint32_t nk = __reduce_add_sync(0xffffffffu, c);
         uint32_t inc = c;
 #pragma unroll
@@ -1320,11 +1330,11 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
         /* Only in the shard's last sync tile can the stream end inside a subsequence, or the shard's last
          * codeword be cut off (its symbol is then not part of total_valid): everywhere else every
          * subsequence is whole and every symbol valid, and the 64-bit bookkeeping is skipped. */
-        uint32_t lim = S, nvalid = nk;
+        uint32_t lim = SPL * S, nvalid = nk;                /* owned bits of my SPL subsequences */
         bool full_out = false;
         if (u + WT >= nunits || !cap_ok) {
-            const uint64_t sub0 = ((uint64_t)u * 32u + lane) * S;
-            lim = sub0 >= a.bits_own ? 0u : (a.bits_own - sub0 < S ? (uint32_t)(a.bits_own - sub0) : S);
+            const uint64_t sub0 = ((uint64_t)u * UNIT + lane * SPL) * S;
+            lim = sub0 >= a.bits_own ? 0u : (a.bits_own - sub0 < SPL * S ? (uint32_t)(a.bits_own - sub0) : SPL * S);
             if (Bt >= total_valid) nvalid = 0;
             else if (total_valid - Bt < nk) nvalid = (uint32_t)(total_valid - Bt);
             full_out = Bt + nvalid > out_capacity;
@@ -1344,8 +1354,23 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
             tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim != S) hb_emit_clipped32<WPT, ADD>(tb, w, lim, e, c, dst);
-                else tl = hb_emit_words32<WPT, ADD>(tb, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                if (lim != SPL * S) {
+                    /* the stream ends inside this lane's bits: every subsequence on its own, byte stores */
+                    hb_emit_clipped32<WPT, ADD>(tb, w, lim < S ? lim : S, e, c0, dst);
+                    if (SPL == 2) {
+                        load_words(p_words + WPT);
+                        hb_emit_clipped32<WPT, ADD>(tb, w, lim > S ? lim - S : 0u, (sub >> 16) & 31u, c - c0, dst + c0);
+                    }
+                } else {
+                    hb_w32 st;
+                    hb_w32_begin(st, e, dst, (uint32_t)(uintptr_t)dst & 3u);
+#pragma unroll 1
+                    for (int h = 0; h < SPL; h++) {
+                        if (h) load_words(p_words + WPT);
+                        hb_emit_words32_part<WPT, ADD>(tb, w, st, c, dst, h == SPL - 1);
+                    }
+                    tl = hb_w32_tail(st);
+                }
             }
             /* the window ends behind its last thread's slice (or with the warp tile) */
             const uint32_t cross = __ballot_sync(0xffffffffu, mine && o + c - wb >= win && o + c < nk);

@@ -113,6 +113,9 @@ int  hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies);
 #define HB_EMIT_WORDS32W 5 /* hb_emit32w_kernel: the same probes, every warp on its own (own staging slice, own bulk
                              store, no block-level barriers) */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
+/* HB_EMIT_WORDS32W: consecutive subsequences a lane decodes in one go (1 or 2; default 1: 2 was measured
+ * slower).  A/B knob. */
+int  hb_ctx_set_emit_lane_subsequences(hb_ctx *ctx, int n);
 /* name of the emit kernel the last decode used for the bulk of its tiles ("" before the first) */
 const char *hb_ctx_last_emit_kernel(const hb_ctx *ctx);
 /* EP-table of the flat emit kernel: index width in bits (8..12, 0 = automatic) and log2 of the

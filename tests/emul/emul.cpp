@@ -429,19 +429,26 @@ struct Emul {
         return true;
     }
 
-    /* mirrors hb_emit32w_kernel, one tile: every group of 32 subsequences (a warp) on its own, with its
-     * own output base (tile base + the symbols in front of it), windows and copy-out */
+    /* mirrors hb_emit32w_kernel, one tile: every group of 32 lanes (a warp) on its own, SPL consecutive
+     * subsequences per lane, with its own output base (tile base + the symbols in front of it), windows
+     * and copy-out */
+    template <int SPL>
     bool emit_tile_warp(uint32_t tile, uint8_t *out, uint64_t out_capacity, uint32_t win, uint32_t stage_bytes,
                         uint64_t total_valid) {
         const uint64_t tile_bit0 = (uint64_t)tile * TS;
-        constexpr int L = T >= 32 ? 32 : T;             /* lanes per warp tile */
+        constexpr int L = T / SPL >= 32 ? 32 : T / SPL;      /* lanes per warp tile */
         uint32_t front = 0;
-        for (int q = 0; q < T / L; q++) {
-            const int t0 = q * L;
+        for (int q = 0; q < T / (L * SPL); q++) {
+            const int t0 = q * L * SPL;
             const uint64_t B = tile_base[tile] + front;
             uint32_t o_acc = 0;
-            std::vector<uint32_t> off(L), cnt(L);
-            for (int l = 0; l < L; l++) { off[l] = o_acc; cnt[l] = hb_sub_count(subs[(uint64_t)tile * T + t0 + l]); o_acc += cnt[l]; }
+            std::vector<uint32_t> off(L), cnt(L), cnt0(L);
+            for (int l = 0; l < L; l++) {
+                off[l] = o_acc;
+                cnt0[l] = hb_sub_count(subs[(uint64_t)tile * T + t0 + l * SPL]);
+                cnt[l] = cnt0[l] + (SPL == 2 ? hb_sub_count(subs[(uint64_t)tile * T + t0 + l * SPL + 1]) : 0u);
+                o_acc += cnt[l];
+            }
             const uint32_t nk = o_acc;
             front += nk;
             uint32_t nvalid = nk;
@@ -455,12 +462,13 @@ struct Emul {
                 uint32_t hi_b = nk;
                 std::vector<hb_tail> tails;
                 for (int l = 0; l < L; l++) {
-                    const int t = t0 + l;
-                    const uint32_t o = off[l], c = cnt[l];
+                    const int t = t0 + l * SPL;
+                    const uint32_t o = off[l], c = cnt[l], c0 = cnt0[l];
                     const bool mine = c && o >= wb && o - wb < win;
                     if (!mine) continue;
                     const uint64_t sub0 = tile_bit0 + (uint64_t)t * S;
-                    const uint32_t lim = sub0 >= bits_own ? 0u : (bits_own - sub0 < S ? (uint32_t)(bits_own - sub0) : S);
+                    const uint32_t lim = sub0 >= bits_own ? 0u
+                                       : (bits_own - sub0 < SPL * S ? (uint32_t)(bits_own - sub0) : SPL * S);
                     const uint32_t e = hb_sub_entry(subs[(uint64_t)tile * T + t]);
                     if (al + (o - wb) + c > stage_bytes) return false;      /* staging bound violated */
                     uint32_t w[WPT + 1];
@@ -469,9 +477,23 @@ struct Emul {
                     const uint8_t canary = dst[c];
                     const uint32_t mis = (al + (o - wb)) & 3u;
                     uint32_t n = c;
-                    if (lim != S || WPT < 2) n = hb_emit_clipped32<WPT>(tbE32, w, lim, e, c, dst);
-                    else if constexpr (WPT >= 2) {
-                        tails.push_back(hb_emit_words32<WPT>(tbE32, w, e, c, dst, mis));
+                    if (lim != SPL * S || WPT < 2) {
+                        n = hb_emit_clipped32<WPT>(tbE32, w, lim < S ? lim : S, e, c0, dst);
+                        if (SPL == 2) {
+                            load((uint64_t)tile * (T * WPT) + (uint64_t)(t + 1) * WPT, w);
+                            n += hb_emit_clipped32<WPT>(tbE32, w, lim > S ? lim - S : 0u,
+                                                        hb_sub_entry(subs[(uint64_t)tile * T + t + 1]), c - c0, dst + c0);
+                        }
+                    } else if constexpr (WPT >= 2) {
+                        hb_w32 st;
+                        hb_w32_begin(st, e, dst, mis);
+                        for (int h = 0; h < SPL; h++) {
+                            /* the chain runs on (its last probe may already have taken codewords that start
+                             * in the second subsequence: st.acc is a probe position, not the recorded entry) */
+                            if (h) load((uint64_t)tile * (T * WPT) + (uint64_t)(t + 1) * WPT, w);
+                            hb_emit_words32_part<WPT>(tbE32, w, st, c, dst, h == SPL - 1);
+                        }
+                        tails.push_back(hb_w32_tail(st));
                         if ((uint32_t)((tails.back().at + tails.back().k) - dst) != c) return false;
                     }
                     if (n != c) return false;
@@ -588,7 +610,7 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
     E.tbS = hb_tables{stab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE = hb_tables{etab, 0u, ((1u << wf) - 1u) << 2, slow};
     E.tbE64 = hb_tables64{e64, 0u, ((1u << wf64) - 1u) << 3, slow, 3u, 0u};
-    if (emit_mode == 3 || emit_mode == 4) {   /* E32-table exactly as hb_emit32_kernel builds it (index width: ep_wf, else wf64) */
+    if (emit_mode >= 3 && emit_mode <= 5) {   /* E32-table exactly as hb_emit32_kernel builds it (index width: ep_wf, else wf64) */
         uint32_t wf32 = ep_wf ? ep_wf : wf64;
         if (wf32 > maxlen && maxlen >= 9u) wf32 = maxlen;
         E.e32tab.resize((size_t)1 << wf32);
@@ -622,11 +644,16 @@ static int run(const uint32_t *lut_entries, uint32_t w1, uint32_t maxlen, uint32
         }
         for (uint32_t tile = 0; tile < E.ntiles; tile++) {
             const bool flat = E.flat && tile + 1 < E.ntiles;
-            if (emit_mode == 4) {    /* warp tiles: a window sized for 32 subsequences */
-                const uint32_t L = T >= 32 ? 32u : (uint32_t)T;
-                uint32_t ww = emit_win ? emit_win : ((L * max_c + 15u) & ~15u);
-                if (ww < ((max_c + 15u) & ~15u)) ww = (max_c + 15u) & ~15u;
-                if (!E.emit_tile_warp(tile, out, out_capacity, ww, (ww + max_c + 32u + 15u) & ~15u, res[0])) { rc = -6; break; }
+            if (emit_mode == 4 || emit_mode == 5) {    /* warp tiles: a window sized for 32 lanes' output */
+                const uint32_t spl = emit_mode == 5 && T >= 2 ? 2u : 1u;
+                const uint32_t L = T / spl >= 32 ? 32u : (uint32_t)T / spl;
+                const uint32_t mc = spl * max_c;
+                uint32_t ww = emit_win ? emit_win : ((L * mc + 15u) & ~15u);
+                if (ww < ((mc + 15u) & ~15u)) ww = (mc + 15u) & ~15u;
+                const uint32_t stg = (ww + mc + 32u + 15u) & ~15u;
+                const bool ok = spl == 2 ? E.template emit_tile_warp<2>(tile, out, out_capacity, ww, stg, res[0])
+                                         : E.template emit_tile_warp<1>(tile, out, out_capacity, ww, stg, res[0]);
+                if (!ok) { rc = -6; break; }
                 continue;
             }
             if (flat ? !E.emit_tile_flat(tile, out, out_capacity, win, stage + 16)

@@ -281,7 +281,7 @@ def test_badly_synchronising_codes(lengths, shape):
     assert rc == 0 and np.array_equal(got, syms)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 3, 4, 5])
 @pytest.mark.parametrize("shape", [(4, 256), (8, 256), (16, 256), (2, 8)])
 @pytest.mark.parametrize("name", ["book2", "world192"])
 def test_emit_paths(name, mode, shape):
@@ -385,7 +385,7 @@ def test_random_codes_and_streams(seed):
         shape = [(4, 256), (8, 256), (16, 256), (2, 8), (1, 4)][int(rng.integers(5))]
         lut = hb.build_lut(tree)
         wds = E.words_of(st.data, (bits + 7) // 8)
-        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=int(rng.choice([0, 1, 3, 3, 4, 4])),
+        out, _, res, _, rc = E.run(lut, wds, bits, bits, *shape, emit_mode=int(rng.choice([0, 1, 3, 4, 5, 5])),
                                    ep_wf=int(rng.choice([0, 9, 10, 12, 13, 14])), out_offset=int(rng.integers(16)))
         tag = (seed, case, nleaves, maxlen, n, shape)
         assert rc == 0 and int(res[0]) == n, tag
@@ -427,13 +427,14 @@ def test_e32_emit_truncated_and_windows():
         assert rc == 0 and int(res[0]) == want.size
         assert np.array_equal(out[: want.size], want) and np.array_equal(want, full[: want.size])
     for win in (2048, 1008, 144):
-        for mode in (3, 4):     # mode 4: warp tiles (hb_emit32w_kernel), several windows per warp
+        for mode in (3, 4, 5):  # modes 4, 5: warp tiles (hb_emit32w_kernel, one / two subsequences per lane)
             out, _, res, _, rc = E.run(lut, w, st.bits, st.bits, 8, 256, emit_win=win, out_offset=3, emit_mode=mode, ep_wf=0)
             assert rc == 0 and int(res[0]) == st.usize and np.array_equal(out[: st.usize], full)
     for bits in (st.bits - 7, 8 * 4096 + 5, 777):
         want = O.simple_decode(O.Stream(st.tree, st.data, bits, 0))
-        out, _, res, _, rc = E.run(lut, w, bits, bits, 8, 256, emit_mode=4, ep_wf=0, out_offset=5)
-        assert rc == 0 and int(res[0]) == want.size and np.array_equal(out[: want.size], want)
+        for mode in (4, 5):
+            out, _, res, _, rc = E.run(lut, w, bits, bits, 8, 256, emit_mode=mode, ep_wf=0, out_offset=5)
+            assert rc == 0 and int(res[0]) == want.size and np.array_equal(out[: want.size], want)
 
 
 # ---- flat emit walk (hb_emit_flat / hb_emitf_kernel) -----------------------------------
@@ -524,7 +525,7 @@ def test_codes_with_a_common_length_factor(lengths, shape):
     data, bits = O.encode_with_codes(codes, syms)
     st = O.Stream(tree, data, bits, n)
     want = (syms & 255).astype(np.uint8)
-    for mode in (1, 2, 3, 4):
+    for mode in (1, 2, 3, 4, 5):
         got, stats, rc = E.decode(st, *shape, lut=lut, emit_mode=mode)
         assert rc == 0 and np.array_equal(got, want), (mode,)
     # byte-range shards of the same stream (shards start at multiples of 128 bits)

@@ -239,7 +239,7 @@ def test_output_too_small_and_bad_args(ctx, dev):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("path", ["words32w", "words32", "words"])
+@pytest.mark.parametrize("path", ["words32w", "words32w1", "words32", "words"])
 def test_word_store_kernels_edge_cases(dev, path):
     """The word-store emit kernels on the cases that exercise their end-of-stream bookkeeping (forced
     here: the automatic choice uses them for large streams only): streams cut inside a codeword and at
@@ -248,9 +248,12 @@ def test_word_store_kernels_edge_cases(dev, path):
     f = _stream("paper1")
     st = O.Stream(f.tree, f.data, f.bits, f.usize)
     c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    if path == "words32w1":
+        c.set_emit_lane_subsequences(1)
+        path = "words32w"
     c.set_emit_path(path)
     cb = hb.Codebook(c, f.tree)
-    for bits in [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 65535, 65536, 65537, 100001, f.bits - 1]:
+    for bits in [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 512, 513, 8191, 8192, 8193, 65535, 65536, 65537, 100001, f.bits - 1]:
         want = O.simple_decode(st, bits=bits)
         got, res, _ = _decode_dev(c, cb, f, dev, bits=bits, cap=want.size + 8)
         assert res["n_symbols"] == want.size and np.array_equal(got, want), bits
@@ -430,12 +433,16 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0", "words32w", "words32w:12:0", "words32w:15:0"):
+    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0", "words32w", "words32w:12:0", "words32w:15:0", "words32w1", "words32w1:14:0"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         if ":" in path:     # E32-table geometry: index bits, log2(copies)
             _, wf, rs = path.split(":")
             c.set_emit_table(int(wf), int(rs))
-        c.set_emit_path(path.split(":")[0])
+        name0 = path.split(":")[0]
+        if name0 == "words32w1":          # one subsequence per lane instead of two
+            c.set_emit_lane_subsequences(1)
+            name0 = "words32w"
+        c.set_emit_path(name0)
         cb = hb.Codebook(c, f.tree)
         for off in (0, 1, 2, 3, 7):
             got, res, raw = _decode_dev(c, cb, f, dev, out_offset=off)
