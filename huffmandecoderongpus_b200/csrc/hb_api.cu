@@ -547,7 +547,7 @@ static int launch_fsm_sync(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_a
     fa.depth = cb->d_fsm + ns * 512;
     fa.pstep = (const uint16_t *)(cb->d_fsm + ns * 512 + 256);
     fa.nstates = (uint32_t)ns;
-    const size_t table_bytes = ns * 512, extra = 256 + 512;
+    const size_t table_bytes = ns * 512, extra = 256 + 512 + ((size_t)4 << a.w1);   /* + level 1 of the LUT */
     int rc;
     /* on request (A/B, tests): two or four copies of the table on disjoint banks, one CTA of four groups
      * per SM, 8-word subsequences.  Fewer bank-conflict replays, but 32 instead of 48 warps per SM, and the

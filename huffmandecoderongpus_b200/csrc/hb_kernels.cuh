@@ -94,7 +94,9 @@ __device__ __forceinline__ uint32_t hb_first_entry(const hb_stream_args &a, uint
 /* device status word bits */
 #define HB_ST_OUTPUT_FULL 1u
 
-template <int WPT>
+/* EXTRA = false: w[WPT] (the first word of the next subsequence) is left to the caller -- a load of one
+ * word per thread is 9 more tag lookups per warp on the pipe the sync kernel is bound by */
+template <int WPT, bool EXTRA = true>
 __device__ __forceinline__ void hb_load_words(const hb_stream_args &a, uint64_t wbase,
                                               uint32_t (&w)[WPT + 1]) {
     if (wbase + WPT + 1 <= a.nwords) {
@@ -115,10 +117,10 @@ __device__ __forceinline__ void hb_load_words(const hb_stream_args &a, uint64_t 
                 w[4 * v + 0] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
             }
         }
-        w[WPT] = __ldg(a.words + wbase + WPT);
+        if (EXTRA) w[WPT] = __ldg(a.words + wbase + WPT);
     } else {
 #pragma unroll
-        for (int j = 0; j <= WPT; j++)
+        for (int j = 0; j < WPT + (EXTRA ? 1 : 0); j++)
             w[j] = (wbase + j < a.nwords) ? __ldg(a.words + wbase + j) : 0u;
     }
 }
@@ -414,7 +416,8 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
     uint8_t *s_depth = reinterpret_cast<uint8_t *>(smem + fa.nstates * 128u * R);   /* 256 */
     uint16_t *s_pstep = reinterpret_cast<uint16_t *>(smem + fa.nstates * 128u * R + 64u);   /* 256 */
     const uint32_t g = threadIdx.x / T, t = threadIdx.x % T, bar = g + 1u;
-    uint32_t *s_grp = smem + fa.nstates * 128u * R + 192u + g * hb_fsm_group_words<WPT>();
+    uint32_t *s_l1 = smem + fa.nstates * 128u * R + 192u;                  /* level 1 of the single-symbol table */
+    uint32_t *s_grp = s_l1 + (1u << a.w1) + g * hb_fsm_group_words<WPT>();
     uint16_t *s_rec = reinterpret_cast<uint16_t *>(s_grp);                 /* WPT * T records */
     uint32_t *s_cs = s_grp + WPT * T / 2;                                  /* T: prefix of END counts */
     uint32_t *s_exit = s_cs + T;                                           /* T: state behind each subsequence */
@@ -442,6 +445,9 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
             s_depth[i] = __ldg(fa.depth + i);
             s_pstep[i] = __ldg(fa.pstep + i);
         }
+        /* three lanes in four turn their boundary state into a forward offset with one probe of this
+         * table (hb_fsm_fwd): from global memory that was 20 tag lookups per warp and subsequence */
+        for (uint32_t i = threadIdx.x; i < (1u << a.w1); i += G * T) s_l1[i] = __ldg(a.lut + i);
     }
     __syncthreads();
     hb_fsm f;
@@ -451,11 +457,18 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
     f.pstep = s_pstep;
     f.lc = (uint32_t)LC;
     f.cbits = LC ? ((t & (R - 1u)) << (14 - 2 * LC)) * 0x10001u : 0u;
-    const hb_lutref slow{a.lut, a.lut, (1u << a.w1) - 1u};
+    const hb_lutref slow{s_l1, a.lut, (1u << a.w1) - 1u};
 
+    /* w[WPT], the first word behind the subsequence, is only read by the tile's last thread */
+    auto load_tile = [&](uint32_t tl, uint32_t (&w)[WPT + 1]) {
+        const uint64_t wb = (uint64_t)tl * (T * WPT) + (uint64_t)t * WPT;
+        hb_load_words<WPT, false>(a, wb, w);
+        if (t == T - 1) w[WPT] = wb + WPT < a.nwords ? __ldg(a.words + wb + WPT) : 0u;
+    };
     uint32_t tile = blockIdx.x * G + g;
     uint32_t w[WPT + 1];
-    if (tile < ntiles_full) hb_load_words<WPT>(a, (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT, w);
+    w[WPT] = 0u;
+    if (tile < ntiles_full) load_tile(tile, w);
     while (tile < ntiles_full) {
         const uint64_t wbase = (uint64_t)tile * (T * WPT) + (uint64_t)t * WPT;
 
@@ -512,7 +525,7 @@ hb_fsm_sync_kernel(hb_stream_args a, hb_fsm_args fa, uint32_t ntiles_full,
         /* the words are dead from here on: fetch the next tile's now, so that the loads
          * fly during the scan, the hypothesis walks and the barriers */
         const uint32_t next = tile + gridDim.x * G;
-        if (next < ntiles_full) hb_load_words<WPT>(a, (uint64_t)next * (T * WPT) + (uint64_t)t * WPT, w);
+        if (next < ntiles_full) load_tile(next, w);
         uint32_t E0;
         s_cs[t] = hb_group_exscan(ends, s_warp, bar, t, &E0);
         hb_group_sync(bar);
@@ -1284,7 +1297,9 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
                     w[4 * v + 0] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
                 }
             }
-            w[WPT] = __ldg(p_words + WPT);
+            /* SPL = 1: the word behind my subsequence is my right neighbour's first one -- a shuffle at the
+             * top of the unit loop (one wavefront instead of nine tag lookups); only lane 31 loads it */
+            if (SPL != 1 || lane == 31u) w[WPT] = __ldg(p_words + WPT);
         } else {
 #pragma unroll
             for (int j = 0; j <= WPT; j++) w[j] = p_words + j < words_end ? __ldg(p_words + j) : 0u;
@@ -1305,6 +1320,10 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
     };
     if (u < nunits) fetch();
     while (u < nunits) {
+        if (SPL == 1) {
+            const uint32_t nx = __shfl_down_sync(0xffffffffu, w[0], 1);
+            if (lane != 31u) w[WPT] = nx;
+        }
         const uint32_t e = hb_sub_entry((uint16_t)sub), c0 = hb_sub_count((uint16_t)sub);
         const uint32_t c = c0 + (SPL == 2 ? sub >> 21 : 0u);
         /* symbols of the sync tile's subsequences in front of this warp tile: the sum over the lanes below
