@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--ep-wf", type=int, default=0, help="EP-table index bits of the flat emit kernel (0 = auto)")
     ap.add_argument("--ep-copies-log2", type=int, default=-1, help="log2 of the EP-table copies (-1 = auto)")
-    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat", "words32", "words32w"],
+    ap.add_argument("--emit-path", default="auto", choices=["auto", "bytes", "words", "flat", "words32", "words32w", "words64w"],
                     help="emit kernel A/B (auto = words)")
     ap.add_argument("--emit-spl", type=int, default=1, choices=[1, 2], help="subsequences per lane of the warp-autonomous emit kernel")
     ap.add_argument("--sync-copies-log2", type=int, default=-1, help="transducer table copies in the sync kernel (log2; -1 = auto)")

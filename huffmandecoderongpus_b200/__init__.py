@@ -327,7 +327,7 @@ class Context:
         """emit kernel: "bytes" (byte stores), "words" (whole 32-bit words, one loop per stream
         word), "flat" (hb_emitf_kernel on every tile but the last; experimental, slower) or
         "auto" (= words)."""
-        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2, "flat": 3, "words32": 4, "words32w": 5}[path]),
+        _check(lib().hb_ctx_set_emit_path(self.h, {"auto": 0, "bytes": 1, "words": 2, "flat": 3, "words32": 4, "words32w": 5, "words64w": 6}[path]),
                "hb_ctx_set_emit_path")
 
     def set_emit_table(self, index_bits=0, log2_copies=-1):

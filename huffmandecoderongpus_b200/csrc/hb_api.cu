@@ -256,7 +256,7 @@ extern "C" int hb_ctx_set_phase_timing(hb_ctx *ctx, int mode) {
 
 extern "C" int hb_ctx_set_emit_path(hb_ctx *ctx, int path) {
     if (!ctx || (path != HB_EMIT_AUTO && path != HB_EMIT_BYTES && path != HB_EMIT_WORDS && path != HB_EMIT_FLAT &&
-                 path != HB_EMIT_WORDS32 && path != HB_EMIT_WORDS32W))
+                 path != HB_EMIT_WORDS32 && path != HB_EMIT_WORDS32W && path != HB_EMIT_WORDS64W))
         return HB_ERR_ARG;
     ctx->emit_path = path;
     return HB_OK;
@@ -828,9 +828,49 @@ static int launch_emit(hb_ctx *ctx, const hb_codebook *cb, const hb_stream_args 
     /* 32-bit table entries, three symbols per probe, 4 (or 8) copies on disjoint banks, the table
      * at a multiple of its size (hb_emit32_kernel): streams of at least four tiles per SM */
     bool done32 = false;
-    const bool want32w = ctx->emit_path == HB_EMIT_WORDS32W ||
+    /* warp-autonomous pipeline over the E64-table (four symbols per probe): on request, and by default for codes
+     * whose implied mean length is at most 3.5 bits (three symbols do not fill a probe there) in streams of at
+     * least four tiles per SM: fib4g emit 1.681 -> 1.568 ms with 11 bits x 4 copies (12 x 2: 1.605, 10 x 8: 1.594,
+     * 11 x 2: 1.648); english1g would lose (0.677 against 0.557 ms) */
+    if (WPT >= 2 && tile0 == 0 &&
+        (ctx->emit_path == HB_EMIT_WORDS64W ||
+         (ctx->emit_path == HB_EMIT_AUTO && ctx->auto_warp_emit && cb->lut.wf64 < HB_WF_MAX &&
+          a.ntiles >= 4u * (uint32_t)ctx->prop.multiProcessorCount))) {
+        const size_t limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
+        const uint32_t Sbits = 32u * (uint32_t)WPT;
+        const uint32_t max_c = (Sbits + cb->lut.minlen - 1) / cb->lut.minlen;
+        const double avg = cb->implied_avg_len > 1.0 ? cb->implied_avg_len : 1.0;
+        uint32_t winw = (uint32_t)(32.0 * Sbits * 1.25 / avg) + 64u;
+        if (winw > 32u * max_c) winw = 32u * max_c;
+        if (winw < max_c) winw = max_c;
+        winw = (winw + 15u) & ~15u;
+        const uint32_t stg = (winw + max_c + 32u + 15u) & ~15u;
+        uint32_t wfx = ctx->ep_wf >= 9 && ctx->ep_wf <= 14 ? (uint32_t)ctx->ep_wf : ctx->e64_wide;
+        if (wfx > cb->lut.maxlen && cb->lut.maxlen >= 9u) wfx = cb->lut.maxlen;
+        uint32_t rs = ctx->ep_rshift >= 0 ? (ctx->ep_rshift > 3 ? 3u : (uint32_t)ctx->ep_rshift) : 2u;
+        while (rs > 0 && ((size_t)8 << (wfx + rs)) + 32u * (size_t)stg > limit) rs--;
+        while (wfx > 9u && ((size_t)8 << (wfx + rs)) + 32u * (size_t)stg > limit) wfx--;
+        const size_t tab = (size_t)8 << (wfx + rs), total = tab + 32u * (size_t)stg;
+        /* unasked, only with a table of at least 10 bits beside the whole window; else the group kernels */
+        if (total <= limit && (ctx->emit_path == HB_EMIT_WORDS64W || wfx >= 10u)) {
+            ae.wf = wfx;
+            if (wfx == cb->lut.wf64) ae.fast = a.fast + ((size_t)2 << a.wf);
+            else if ((rc = e64_table(ctx, cb, wfx, &ae.fast))) return rc;
+            const uint64_t units = (uint64_t)a.ntiles * (HB_T / 32u);
+            uint64_t g = (units + 31) / 32;
+            if (g > (uint64_t)ctx->prop.multiProcessorCount) g = (uint64_t)ctx->prop.multiProcessorCount;
+            CK(cudaFuncSetAttribute(hb_emit32w_kernel<WPT, true, 1, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
+            hb_emit32w_kernel<WPT, true, 1, true><<<(int)g, 1024, total, ctx->stream>>>(
+                ae, rs, 0u, (uint32_t)tab, (const uint16_t *)ctx->subs.p, (const uint64_t *)ctx->tile_base.p,
+                (const uint64_t *)(misc + 32), (uint8_t *)d_out, out_capacity, winw, stg, (uint32_t *)(misc + 36));
+            done32 = true;
+            ctx->last_emit = "hb_emit32w_kernel<E64>";
+        }
+    }
+    const bool want32w = !done32 && (ctx->emit_path == HB_EMIT_WORDS32W ||
                          (ctx->emit_path == HB_EMIT_AUTO && ctx->auto_warp_emit &&
-                          a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount);
+                          a.ntiles - tile0 >= 4u * (uint32_t)ctx->prop.multiProcessorCount));
     if (WPT >= 2 && want32w) {
         /* warp-autonomous variant: one staging slice per warp (32 subsequences' worth of output, 25 % head
          * room, one thread's overhang), the table in front of the slices */

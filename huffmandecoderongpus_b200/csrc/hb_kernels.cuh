@@ -1223,7 +1223,10 @@ hb_emit32_kernel(hb_stream_args a, uint32_t tile0, uint32_t rshift, uint32_t tab
  * per-warp-tile prologue and epilogue -- 40 % of the kernel's instructions with SPL = 1 -- are paid once per
  * 512 stream bits instead of once per 256.  The second subsequence's words are loaded when the first is done.
  * Byte-exact, but measured slower than SPL = 1 (english1g 0.628 against 0.558 ms): an A/B path. */
-template <int WPT, bool ADD, int SPL>
+/* E64 = true: the same warp-autonomous pipeline over the E64-table (up to FOUR symbols per probe, LDS.64; a.wf
+ * index bits, 1 << rshift copies interleaved entry by entry as in hb_emitw_kernel) -- for codes so short that
+ * three symbols do not fill a probe (the Fibonacci-skewed model: 2.6 bits per symbol).  SPL = 1 only. */
+template <int WPT, bool ADD, int SPL, bool E64 = false>
 __global__ void __launch_bounds__(1024, 1)
 hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t stage_off,
                   const uint16_t *__restrict__ subs, const uint64_t *__restrict__ tile_base,
@@ -1235,15 +1238,19 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
     constexpr uint32_t WT = T / UNIT;                       /* warp tiles per sync tile */
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tab_bytes = 4u << (a.wf + rshift);
+    const uint32_t tab_bytes = (E64 ? 8u : 4u) << (a.wf + rshift);
     uint32_t *s_fast = smem + tab_off / 4u;
     uint8_t *s_out = reinterpret_cast<uint8_t *>(smem) + stage_off + warp * stage_bytes;   /* 16-aligned */
     const uint32_t tab_saddr = (uint32_t)__cvta_generic_to_shared(s_fast);
-    if (!ADD && (tab_saddr & (tab_bytes - 1u))) {
+    if (!E64 && !ADD && (tab_saddr & (tab_bytes - 1u))) {
         if (threadIdx.x == 0) atomicOr(status, HB_ST_LAYOUT);
         return;
     }
-    if (rshift == 0u) {
+    if (E64) {
+        const uint2 *src = reinterpret_cast<const uint2 *>(a.fast);
+        uint2 *dst = reinterpret_cast<uint2 *>(s_fast);
+        for (uint32_t i = threadIdx.x; i < ((1u << a.wf) << rshift); i += 1024u) dst[i] = __ldg(src + (i >> rshift));
+    } else if (rshift == 0u) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.fast);
         uint4 *dst = reinterpret_cast<uint4 *>(s_fast);
         for (uint32_t i = threadIdx.x; i < (1u << a.wf) / 4u; i += 1024u) dst[i] = __ldg(src + i);
@@ -1262,6 +1269,13 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
     tb.lanebase = hb_opaque((ADD ? 0u : tab_saddr) | ((lane & ((1u << rshift) - 1u)) << 2));
     tb.addbase = hb_opaque(tab_saddr);
     tb.slow = hb_lutref{a.lut, a.lut, (1u << a.w1) - 1u};
+    hb_tables64 tb64;
+    tb64.fast = s_fast;
+    tb64.fast_saddr = hb_opaque(tab_saddr);
+    tb64.sc = 3u + rshift;
+    tb64.fmask = ((1u << a.wf) - 1u) << tb64.sc;
+    tb64.laneoff = hb_opaque(((lane >> (4u - rshift)) & ((1u << rshift) - 1u)) << 3);   /* rshift <= 4 */
+    tb64.slow = tb.slow;
     const uint64_t total_valid = result[0];
     const uint32_t s_out_saddr = hb_opaque((uint32_t)__cvta_generic_to_shared(s_out));
 
@@ -1373,7 +1387,10 @@ hb_emit32w_kernel(hb_stream_args a, uint32_t rshift, uint32_t tab_off, uint32_t 
             tl.k = 0u;
             if (mine) {
                 const hb_out_t dst = (hb_out_t)(s_out_saddr + al + (o - wb));
-                if (lim != SPL * S) {
+                if constexpr (E64) {
+                    if (lim != S) hb_emit_clipped<WPT>(tb64, w, lim, e, c, dst);
+                    else tl = hb_emit_words<WPT>(tb64, w, e, c, dst, (uint32_t)(uintptr_t)dst & 3u);
+                } else if (lim != SPL * S) {
                     /* the stream ends inside this lane's bits: every subsequence on its own, byte stores */
                     hb_emit_clipped32<WPT, ADD>(tb, w, lim < S ? lim : S, e, c0, dst);
                     if (SPL == 2) {

@@ -112,6 +112,8 @@ int  hb_ctx_set_sync_copies(hb_ctx *ctx, int log2_copies);
                              (or 8) copies of the table on disjoint banks */
 #define HB_EMIT_WORDS32W 5 /* hb_emit32w_kernel: the same probes, every warp on its own (own staging slice, own bulk
                              store, no block-level barriers) */
+#define HB_EMIT_WORDS64W 6 /* hb_emit32w_kernel<E64>: the warp-autonomous pipeline over the E64-table (up to four
+                             symbols per probe): codes so short that three symbols do not fill a probe */
 int  hb_ctx_set_emit_path(hb_ctx *ctx, int path);
 /* HB_EMIT_WORDS32W: consecutive subsequences a lane decodes in one go (1 or 2; default 1: 2 was measured
  * slower).  A/B knob. */

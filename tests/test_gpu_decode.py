@@ -239,7 +239,7 @@ def test_output_too_small_and_bad_args(ctx, dev):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("path", ["words32w", "words32w1", "words32", "words"])
+@pytest.mark.parametrize("path", ["words32w", "words32w1", "words64w", "words32", "words"])
 def test_word_store_kernels_edge_cases(dev, path):
     """The word-store emit kernels on the cases that exercise their end-of-stream bookkeeping (forced
     here: the automatic choice uses them for large streams only): streams cut inside a codeword and at
@@ -433,7 +433,8 @@ def test_emit_paths_agree(dev, name, wpt):
     """word-granular staging stores (E64-table, default where the code length allows) and
     byte stores (E-table) give the same bytes, at every output alignment"""
     f = _stream(name)
-    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0", "words32w", "words32w:12:0", "words32w:15:0", "words32w1", "words32w1:14:0"):
+    for path in ("words", "bytes", "auto", "flat", "words32", "words32:11:3", "words32:9:1", "words32:14:0", "words32:13:1", "words32:15:0", "words32w", "words32w:12:0", "words32w:15:0", "words32w1", "words32w1:14:0",
+                 "words64w", "words64w:11:2", "words64w:12:0", "words64w:9:3"):
         c = hb.Context(0, stream=torch.cuda.current_stream().cuda_stream, words_per_thread=wpt)
         if ":" in path:     # E32-table geometry: index bits, log2(copies)
             _, wf, rs = path.split(":")

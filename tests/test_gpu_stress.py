@@ -39,7 +39,7 @@ def test_random_codes_and_streams(seed):
         ctx.set_sync_path(str(rng.choice(["auto", "fsm", "probe"])))
         ctx.set_sync_copies(int(rng.choice([-1, 0, 1, 2])))
         ctx.set_emit_lane_subsequences(int(rng.choice([1, 2])))
-        ctx.set_emit_path(str(rng.choice(["auto", "bytes", "flat", "words", "words32", "words32", "words32w", "words32w"])))
+        ctx.set_emit_path(str(rng.choice(["auto", "bytes", "flat", "words", "words32", "words32", "words32w", "words32w", "words64w"])))
         ctx.set_emit_table(int(rng.choice([0, 9, 10, 11, 12, 13, 14, 15])), int(rng.choice([-1, 3, 2, 0])))
         cb = hb.Codebook(ctx, tree)
         nb = (bits + 7) // 8
