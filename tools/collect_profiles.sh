@@ -1,5 +1,5 @@
 # Round-2 evidence, one gpurun call on one B200:  bash tools/collect_profiles.sh [tag]   (default tag r02j)
-T=${1:-r02j}; mkdir -p gpurun_out/$T; O=gpurun_out/$T
+T=${1:-r02l}; mkdir -p gpurun_out/$T; O=gpurun_out/$T
 git rev-parse HEAD > $O/commit.txt 2>/dev/null || true
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/smi.txt
 python bench.py > $O/bench_default.log 2>&1
