@@ -1,5 +1,5 @@
 # usage: bash tools/scaling_run.sh N   (on a box with N GPUs)
-n=$1; O=gpurun_out/r02k; mkdir -p $O
+n=$1; O=gpurun_out/r02m; mkdir -p $O
 nvidia-smi -L | wc -l
 (time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 30 --warmup 3) > $O/bench_n$n.log 2>&1; echo "rc $?" >> $O/bench_n$n.log
 grep '^{' $O/bench_n$n.log | python -c "
