@@ -3,10 +3,12 @@
  *
  * The reference has no multi-GPU path; SURVEY.md 8(b)(3)/8(e) ask for one under the approach
  * table.  A stream is cut into N contiguous byte ranges (16-byte aligned, 16-byte halo); every
- * device computes its shard's 32-entry transfer map (hb_shard_map), the maps of the shards to
- * its left are copied over (cudaMemcpyPeerAsync, 256 B each, ordered by events: no NCCL, no
- * host round trip), composed on the device (hb_shard_compose) and the shard is emitted into
- * the device's own output slice (hb_shard_emit).  Nothing here decodes on the CPU.
+ * device computes its shard's 32-entry transfer map (hb_shard_map) and stores it straight into
+ * the map tables of the devices to its right over NVLink (hb_push_map_kernel: peer stores, one
+ * launch; where a pair of devices has no peer access the right-hand device pulls the 256 bytes
+ * with cudaMemcpyPeerAsync instead), ordered by events: no NCCL, no host round trip.  Every
+ * device composes the maps to its left (hb_shard_compose) and emits its shard into its own
+ * output slice (hb_shard_emit).  Nothing here decodes on the CPU.
  *
  * Two ways in:
  *   resident   hb_multi_load / hb_multi_generate, then hb_multi_decode (device-timed: CUDA
@@ -62,8 +64,19 @@ struct hb_pool {
     bool quit = false;
 };
 
+struct hb_peer_maps { uint64_t *p[HB_MULTI_MAX]; };
+
+/* device i's map (32 words) into slot i of the map tables of the devices to its right: warp w of
+ * the one CTA serves peer w.  The stores travel over NVLink; the event recorded behind this kernel
+ * is what the receivers' streams wait for. */
+__global__ void hb_push_map_kernel(const uint64_t *__restrict__ src, hb_peer_maps dst, int n_peers) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < n_peers) dst.p[w][l] = src[l];
+}
+
 struct hb_multi {
     int n = 0;
+    bool push_ok = false;          /* every device can store into every other device's memory */
     hb_pool *pool = nullptr;
     std::atomic<uint64_t> map_issued[HB_MULTI_MAX];   /* run number whose ev_map record has been queued */
     std::atomic<int> abort_run{0};
@@ -210,16 +223,24 @@ extern "C" int hb_multi_create(const int *devices, int n_devices, hb_multi **out
         if (e == cudaSuccess) e = cudaMallocHost((void **)&v.h_eb, sizeof(uint64_t) * 4);
         if (e != cudaSuccess) { cudaGetLastError(); hb_multi_destroy(m); return HB_ERR_CUDA; }
     }
-    /* direct peer copies where the topology allows them (the 256-byte map copies work either way) */
+    /* peer access where the topology allows it: maps are then pushed by a kernel (peer stores);
+     * otherwise pulled by 256-byte peer copies, which work either way */
+    bool all_peers = m->n > 1;
     for (int i = 0; i < m->n; i++) {
         cudaSetDevice(m->d[i].device);
         for (int j = 0; j < m->n; j++) {
+            if (i == j) continue;
             int can = 0;
-            if (i != j && cudaDeviceCanAccessPeer(&can, m->d[i].device, m->d[j].device) == cudaSuccess && can)
-                cudaDeviceEnablePeerAccess(m->d[j].device, 0);
+            bool ok = false;
+            if (cudaDeviceCanAccessPeer(&can, m->d[i].device, m->d[j].device) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(m->d[j].device, 0);
+                ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+            }
+            if (!ok) all_peers = false;
         }
     }
     cudaGetLastError();
+    m->push_ok = all_peers && !(getenv("HB_MULTI_PUSH") && getenv("HB_MULTI_PUSH")[0] == '0');
     for (int i = 0; i < HB_MULTI_MAX; i++) m->map_issued[i].store(0);
     if (m->n > 1 && !(getenv("HB_MULTI_THREADS") && getenv("HB_MULTI_THREADS")[0] == '0')) {
         m->pool = new (std::nothrow) hb_pool();
@@ -321,6 +342,13 @@ static int dev_map(hb_multi *m, int i, uint64_t run, bool upload, const uint8_t 
     rc = e == cudaSuccess ? hb_ctx_set_shard_origin(v.ctx, v.a, 1) : HB_ERR_CUDA;
     if (rc == HB_OK)
         rc = hb_shard_map(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_maps + 32 * i);
+    if (rc == HB_OK && m->push_ok && i + 1 < m->n_active) {
+        hb_peer_maps pm;
+        int np = 0;
+        for (int r = i + 1; r < m->n_active; r++) pm.p[np++] = m->d[r].d_maps + 32 * i;
+        hb_push_map_kernel<<<1, 32 * np, 0, v.stream>>>(v.d_maps + 32 * i, pm, np);
+        if ((e = cudaGetLastError()) != cudaSuccess) rc = HB_ERR_CUDA;
+    }
     if (rc == HB_OK && (e = cudaEventRecord(v.ev_map, v.stream)) != cudaSuccess) rc = HB_ERR_CUDA;
     if (rc != HB_OK) m->abort_run.store(1);
     m->map_issued[i].store(run, std::memory_order_release);   /* even on failure: nobody may wait for ever */
@@ -330,8 +358,9 @@ static int dev_map(hb_multi *m, int i, uint64_t run, bool upload, const uint8_t 
         while (m->map_issued[r].load(std::memory_order_acquire) != run) std::this_thread::yield();
         if (m->abort_run.load()) return HB_ERR_STATE;
         DCK(cudaStreamWaitEvent(v.stream, m->d[r].ev_map, 0));
-        DCK(cudaMemcpyPeerAsync(v.d_maps + 32 * r, v.device, m->d[r].d_maps + 32 * r, m->d[r].device,
-                                32 * sizeof(uint64_t), v.stream));
+        if (!m->push_ok)
+            DCK(cudaMemcpyPeerAsync(v.d_maps + 32 * r, v.device, m->d[r].d_maps + 32 * r, m->d[r].device,
+                                    32 * sizeof(uint64_t), v.stream));
     }
     if ((rc = hb_shard_compose(v.ctx, v.d_maps, i + 1, i, v.d_eb))) return dev_fail(m, i, rc, "hb_shard_compose");
     return HB_OK;
