@@ -31,6 +31,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 SEED = 0x48554646  # "HUFF"
+PEER = {"on": False, "seq": 0}   # map exchange by peer stores (hb_shard_exchange); seq advances on every rank alike
 WORKLOADS = {
     # name: (model kind, log2 symbols, default scaling, description).  weak: that many symbols
     # per GPU of one N-times-larger stream; strong: that many symbols in total, split over N
@@ -261,13 +262,22 @@ class Job:
                                     self.out.data_ptr(), self.cap, want_result=want_result)
         hb.shard_map(self.ctx, self.cb, c.data_ptr(), c.numel(), self.bits_own, self.bits_avail, self.my_map.data_ptr())
         if self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_maps, self.my_map)
-            hb.shard_compose(self.ctx, self.all_maps.data_ptr(), self.world, self.rank, self.eb.data_ptr())
+            self.exchange()
             ebp = self.eb.data_ptr()
         else:
             ebp = None
         return hb.shard_emit(self.ctx, self.cb, c.data_ptr(), c.numel(), self.bits_own, self.bits_avail, ebp,
                              self.out.data_ptr(), self.cap, want_result=want_result)
+
+    def exchange(self):
+        """shard maps -> this rank's (entry offset, output base): ONE kernel of peer stores over NVLink
+        (hb_shard_exchange) or, with --exchange nccl, NCCL's all-gather + hb_shard_compose"""
+        if PEER["on"]:
+            PEER["seq"] += 1
+            self.hb.shard_exchange(self.ctx, PEER["seq"], self.eb.data_ptr())
+        else:
+            self.dist.all_gather_into_tensor(self.all_maps, self.my_map)
+            self.hb.shard_compose(self.ctx, self.all_maps.data_ptr(), self.world, self.rank, self.eb.data_ptr())
 
     def barrier(self):
         if self.world > 1:
@@ -343,6 +353,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--host-chunk-mib", type=int, default=0,
                     help="chunk size of the pipelined host path (0 = library default)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the 32-entry shard maps travel -- one kernel of peer stores over NVLink "
+                         "(hb_shard_exchange) or NCCL all-gather + hb_shard_compose")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads")
@@ -382,6 +395,20 @@ def main():
         ctx.set_host_chunk(args.host_chunk_mib << 20)
     ctx.set_emit_path(args.emit_path)
     ctx.set_emit_table(args.ep_wf, args.ep_copies_log2)
+    if world > 1 and args.exchange == "peer":
+        # exchange tables: one 64-byte IPC handle per rank, passed around once; all ranks or none
+        ok = 1
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, hb.peer_export(ctx))
+            hb.peer_connect(ctx, rank, handles)
+        except Exception as e:                      # no IPC / no peer access on this box: NCCL
+            print(f"rank {rank}: peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        dist.barrier()
+        PEER["on"] = bool(int(t[0]))
 
     job = Job(args, ctx, args.workload, scaling, world, rank, dev)
     model, n_total, n_mine = job.model, job.n_total, job.n_mine
@@ -437,8 +464,7 @@ def main():
                 return hb.decode_host(ctx, model.tree, hc, job.bits_total, ho)
             # one process per GPU: upload + map | all-gather of the maps | compose, emit + download
             hb.shard_map_host(ctx, job.cb, hc, job.halo_bytes, job.bits_own, job.bits_avail, job.my_map.data_ptr())
-            dist.all_gather_into_tensor(job.all_maps, job.my_map)
-            hb.shard_compose(ctx, job.all_maps.data_ptr(), world, rank, job.eb.data_ptr())
+            job.exchange()
             return hb.shard_emit_host(ctx, job.cb, job.eb.data_ptr(), ho)
 
         r = e2e_step()
@@ -462,8 +488,9 @@ def main():
                "steps": steps_e, "ms_per_step": dt / steps_e * 1e3,
                "verified": "all output bytes of every rank",
                "path": "hb_decode_host (pinned host buffers, chunked upload/decode/download overlap)" if world == 1
-                       else "per rank: hb_shard_map_host (pinned H2D + map) | all_gather of 32-entry maps | "
-                            "hb_shard_compose + hb_shard_emit_host (emit + pinned D2H)"}
+                       else "per rank: hb_shard_map_host (pinned H2D + map) | " +
+                            ("hb_shard_exchange (peer stores) | " if PEER["on"] else "all_gather of 32-entry maps + hb_shard_compose | ") +
+                            "hb_shard_emit_host (emit + pinned D2H)"}
         del h_comp, h_out, hc, ho
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----------------------
@@ -512,7 +539,8 @@ def main():
                        "symbols_total": head["symbols_total"], "compressed_bytes_total": head["compressed_bytes_total"],
                        "bits_total": head["bits_total"], "max_code_length": head["max_code_length"],
                        "words_per_thread": args.wpt or 8, "sync_path": args.sync_path, "emit_path": args.emit_path,
-                       "parallelism": f"byte-range shards x{world}, 1 NCCL all-gather of 32-entry maps" if world > 1 else "single GPU",
+                       "parallelism": (f"byte-range shards x{world}, maps exchanged by one kernel of peer stores over NVLink (hb_shard_exchange)"
+                                       if PEER["on"] else f"byte-range shards x{world}, 1 NCCL all-gather of 32-entry maps") if world > 1 else "single GPU",
                        "l2": "inputs and outputs larger than L2 (no flush needed)",
                        "compressed_input_GB_per_s": in_gbs},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

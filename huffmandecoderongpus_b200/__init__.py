@@ -151,6 +151,11 @@ def lib():
     L.hb_decode_onethread.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
     L.hb_shard_map.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.hb_shard_compose.argtypes = [vp, vp, i32, i32, vp]
+    L.hb_peer_export.argtypes = [vp, vp]
+    L.hb_peer_connect.argtypes = [vp, i32, i32, vp]
+    L.hb_peer_connect_local.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.hb_shard_exchange.argtypes = [vp, u64, vp]
+    L.hb_peer_close.argtypes = [vp]
     L.hb_shard_emit.argtypes = [vp, vp, vp, u64, u64, u64, vp, vp, u64, C.POINTER(Result)]
     L.hb_decode_host.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
     L.hb_huff_load.argtypes = [C.c_char_p, C.POINTER(HuffFileC)]
@@ -443,6 +448,36 @@ def shard_map(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_map):
 def shard_compose(ctx, d_all_maps, n_ranks, rank, d_entry_base):
     _check(lib().hb_shard_compose(ctx.h, d_all_maps, n_ranks, rank, d_entry_base),
            "hb_shard_compose", ctx.h)
+
+
+PEER_HANDLE_BYTES = 64
+
+
+def peer_export(ctx) -> bytes:
+    """hb_peer_export: the 64-byte IPC handle of this rank's exchange table (pass it to every rank)."""
+    buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+    _check(lib().hb_peer_export(ctx.h, buf), "hb_peer_export", ctx.h)
+    return buf.raw
+
+
+def peer_connect(ctx, rank: int, handles) -> None:
+    """hb_peer_connect: handles = the exported handles of all ranks, in rank order.  The caller must
+    put a barrier between this call and the first shard_exchange."""
+    blob = b"".join(handles)
+    assert len(blob) == PEER_HANDLE_BYTES * len(handles)
+    _check(lib().hb_peer_connect(ctx.h, rank, len(handles), blob), "hb_peer_connect", ctx.h)
+
+
+def peer_connect_local(ctxs) -> None:
+    """hb_peer_connect_local for contexts of this process: ctxs[r] is rank r."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    for r, c in enumerate(ctxs):
+        _check(lib().hb_peer_connect_local(c.h, r, len(ctxs), arr), "hb_peer_connect_local", c.h)
+
+
+def shard_exchange(ctx, seq: int, d_entry_base: int) -> None:
+    """hb_shard_exchange: between shard_map and shard_emit; replaces all-gather + shard_compose."""
+    _check(lib().hb_shard_exchange(ctx.h, seq, d_entry_base), "hb_shard_exchange", ctx.h)
 
 
 def shard_emit(ctx, cb, d_comp, comp_bytes, bits_own, bits_avail, d_entry_base, d_out,

@@ -89,6 +89,11 @@ struct hb_ctx {
     uint64_t hs_readable = 0, hs_own = 0, hs_avail = 0;   /* shard of the last hb_shard_map_host */
     bool origin_known = false;    /* hb_ctx_set_shard_origin */
     uint64_t origin_byte = 0;
+    /* map exchange by peer stores (hb_peer_*, one process per GPU) */
+    uint64_t *peer_tab = nullptr;                 /* this rank's exchange table (cudaMalloc: exportable) */
+    uint64_t *peer_ptr[HB_MULTI_MAX] = {};        /* tables of the ranks to the right, opened from their handles */
+    int peer_rank = -1, peer_n = 0;
+    bool peer_ipc = false;                        /* peer_ptr came from cudaIpcOpenMemHandle */
 };
 
 static const char *const k_errs[] = {
@@ -213,6 +218,7 @@ extern "C" void hb_ctx_destroy(hb_ctx *ctx) {
     for (int i = 0; i < ctx->tim_cap * HB_NEV; i++) cudaEventDestroy(ctx->tim_ev[i]);
     free(ctx->tim_ev);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    hb_peer_close(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1082,6 +1088,154 @@ extern "C" int hb_shard_compose(hb_ctx *ctx, const uint64_t *d_all_maps, int n_r
     return HB_OK;
 }
 
+/* ---- map exchange without NCCL: one process per GPU, peer stores over NVLink ------------------
+ * Every rank owns an exchange table in its own memory: HB_PEER_DEPTH ring slots x HB_MULTI_MAX
+ * source ranks x (32 map words + a sequence flag).  hb_exchange_kernel, launched behind the scan of
+ * hb_shard_map, (1) stores this rank's map into slot seq % DEPTH of the tables of the ranks to its
+ * RIGHT (warp w serves rank + 1 + w; relaxed system-scope stores, a system fence, then the flag with
+ * release semantics) and (2) has one thread wait for the flags of the ranks to its LEFT in its own
+ * table and compose their maps into (entry offset, output base) -- what NCCL's all-gather plus
+ * hb_compose_kernel did in two launches and ~30 us.  Rank 0 waits for nobody and every rank stores
+ * before it waits, so the chain cannot deadlock; a rank that never shows up is reported after 5 s
+ * (HB_ST_PEER_TIMEOUT -> HB_ERR_STATE) instead of hanging the device.  The ring lets a rank run up
+ * to HB_PEER_DEPTH - 1 decodes ahead of its neighbours without overwriting a map not yet read. */
+#define HB_PEER_DEPTH 1024u
+#define HB_PEER_SLOT 40u
+#define HB_ST_PEER_TIMEOUT 4u
+struct hb_peer_tabs { uint64_t *p[HB_MULTI_MAX]; };
+
+__global__ void __launch_bounds__(256)
+hb_exchange_kernel(const uint64_t *__restrict__ my_map, hb_peer_tabs tabs, const uint64_t *own_tab, int rank,
+                   int n_ranks, uint64_t seq, uint64_t *__restrict__ entry_base, uint32_t *__restrict__ status) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const size_t ring = (size_t)(seq % HB_PEER_DEPTH) * HB_MULTI_MAX * HB_PEER_SLOT;
+    const int dst = rank + 1 + w;
+    if (dst < n_ranks) {
+        uint64_t *t = tabs.p[dst] + ring + (size_t)rank * HB_PEER_SLOT;
+        const uint64_t v = my_map[l];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(t + l), "l"(v) : "memory");
+        __threadfence_system();
+        __syncwarp();
+        if (l == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(t + 32), "l"(seq) : "memory");
+    }
+    if (threadIdx.x == 7 * 32) {     /* at most seven peers: warp 7 never stores */
+        uint32_t cur = 0;
+        uint64_t base = 0, t0, t1;
+        bool ok = true;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int r = 0; r < rank && ok; r++) {
+            const uint64_t *sl = own_tab + ring + (size_t)r * HB_PEER_SLOT;
+            for (;;) {
+                uint64_t f;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(sl + 32) : "memory");
+                if (f == seq) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 5000000000ull) { ok = false; break; }
+            }
+            if (!ok) break;
+            uint64_t m;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(sl + cur) : "memory");
+            base += m >> 8;
+            cur = (uint32_t)m & 31u;
+        }
+        if (!ok) { atomicOr(status, HB_ST_PEER_TIMEOUT); cur = 0; base = 0; }
+        entry_base[0] = cur;
+        entry_base[1] = base;
+        entry_base[2] = base + (my_map[cur] >> 8);
+    }
+}
+
+extern "C" int hb_peer_close(hb_ctx *ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->peer_tab || ctx->peer_n) cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < HB_MULTI_MAX; r++)
+        if (ctx->peer_ptr[r]) {
+            if (ctx->peer_ipc) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+            ctx->peer_ptr[r] = nullptr;
+        }
+    if (ctx->peer_tab) { cudaFree(ctx->peer_tab); ctx->peer_tab = nullptr; }
+    ctx->peer_rank = -1;
+    ctx->peer_n = 0;
+    cudaGetLastError();
+    return HB_OK;
+}
+
+static int peer_table(hb_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->peer_tab) {
+        const size_t bytes = sizeof(uint64_t) * HB_PEER_DEPTH * HB_MULTI_MAX * HB_PEER_SLOT;
+        CK(cudaMalloc((void **)&ctx->peer_tab, bytes));
+        CK(cudaMemset(ctx->peer_tab, 0, bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    return HB_OK;
+}
+
+extern "C" int hb_peer_export(hb_ctx *ctx, void *handle) {
+    if (!ctx || !handle) return HB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == HB_PEER_HANDLE_BYTES, "IPC handle size");
+    int rc = peer_table(ctx);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->peer_tab));
+    memcpy(handle, &h, sizeof(h));
+    return HB_OK;
+}
+
+extern "C" int hb_peer_connect(hb_ctx *ctx, int rank, int n_ranks, const void *handles) {
+    if (!ctx || !handles || n_ranks < 1 || n_ranks > HB_MULTI_MAX || rank < 0 || rank >= n_ranks) return HB_ERR_ARG;
+    if (!ctx->peer_tab) return HB_ERR_STATE;       /* hb_peer_export first */
+    CK(cudaSetDevice(ctx->device));
+    for (int r = rank + 1; r < n_ranks; r++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)r * HB_PEER_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_ptr[r] = (uint64_t *)p;
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_n = n_ranks;
+    ctx->peer_ipc = true;
+    return HB_OK;
+}
+
+/* the same for contexts of ONE process (several devices, or several contexts on one device: tests) */
+extern "C" int hb_peer_connect_local(hb_ctx *ctx, int rank, int n_ranks, hb_ctx *const *ctxs) {
+    if (!ctx || !ctxs || n_ranks < 1 || n_ranks > HB_MULTI_MAX || rank < 0 || rank >= n_ranks || ctxs[rank] != ctx)
+        return HB_ERR_ARG;
+    int rc = peer_table(ctx);
+    if (rc) return rc;
+    for (int r = rank + 1; r < n_ranks; r++) {
+        if (!ctxs[r]) return HB_ERR_ARG;
+        if ((rc = peer_table(ctxs[r]))) return rc;
+        if (ctxs[r]->device != ctx->device) {
+            CK(cudaSetDevice(ctx->device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[r]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        ctx->peer_ptr[r] = ctxs[r]->peer_tab;
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_n = n_ranks;
+    ctx->peer_ipc = false;
+    return HB_OK;
+}
+
+extern "C" int hb_shard_exchange(hb_ctx *ctx, uint64_t seq, uint64_t *d_entry_base) {
+    if (!ctx || !d_entry_base || seq == 0) return HB_ERR_ARG;
+    if (!ctx->have_map || ctx->peer_rank < 0) return HB_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    hb_peer_tabs tabs;
+    for (int r = 0; r < HB_MULTI_MAX; r++) tabs.p[r] = ctx->peer_ptr[r];
+    uint64_t *misc = misc_words(ctx);
+    hb_exchange_kernel<<<1, 256, 0, ctx->stream>>>(misc, tabs, ctx->peer_tab, ctx->peer_rank, ctx->peer_n, seq,
+                                                   d_entry_base, (uint32_t *)(misc + 36));
+    CK(cudaGetLastError());
+    return HB_OK;
+}
+
 static int finish_result(hb_ctx *ctx, uint32_t ntiles, uint32_t launches, hb_result *res) {
     uint64_t *misc = misc_words(ctx);
     CK(cudaMemcpyAsync(ctx->h_res, misc + 32, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
@@ -1108,6 +1262,10 @@ static int finish_result(hb_ctx *ctx, uint32_t ntiles, uint32_t launches, hb_res
     if ((uint32_t)ctx->h_res[4] & HB_ST_LAYOUT) {
         snprintf(ctx->err, sizeof(ctx->err), "hb_emit32_kernel: table not aligned to its size (dynamic shared memory base moved)");
         return HB_ERR_CUDA;
+    }
+    if ((uint32_t)ctx->h_res[4] & HB_ST_PEER_TIMEOUT) {
+        snprintf(ctx->err, sizeof(ctx->err), "hb_shard_exchange: a rank to the left never delivered its map (5 s)");
+        return HB_ERR_STATE;
     }
     if ((uint32_t)ctx->h_res[4] & HB_ST_OUTPUT_FULL) return HB_ERR_OUTPUT_FULL;
     return HB_OK;

@@ -200,6 +200,24 @@ int hb_shard_map(hb_ctx *ctx, const hb_codebook *cb, const void *d_comp,
  * [2] = total symbols of all ranks.  Asynchronous. */
 int hb_shard_compose(hb_ctx *ctx, const uint64_t *d_all_maps, int n_ranks,
                      int rank, uint64_t *d_entry_base);
+/* The exchange + compose WITHOUT a collective library, for one process per GPU on one NVLink domain:
+ * every rank exports a small exchange table (hb_peer_export: a 64-byte CUDA IPC handle the caller
+ * passes around once, e.g. with torch.distributed / MPI all-gather), opens the tables of the ranks
+ * to its right (hb_peer_connect: handles = n_ranks x 64 bytes, rank-major; a barrier of the caller
+ * must follow before the first exchange), and then, per decode, calls hb_shard_exchange between
+ * hb_shard_map and hb_shard_emit: ONE kernel stores this rank's map into its right neighbours'
+ * tables (peer stores over NVLink), waits for the maps of its left neighbours and writes
+ * d_entry_base[0..2] = entry offset, output base, symbols through this rank.  seq: the same value
+ * on every rank for the same decode, > 0 and increasing by one (a rank may run up to 1023 decodes
+ * ahead of another).  A rank that never delivers is reported by hb_shard_emit / hb_shard_result as
+ * HB_ERR_STATE after 5 s.  Replaces the caller's all-gather + hb_shard_compose. */
+#define HB_PEER_HANDLE_BYTES 64
+int hb_peer_export(hb_ctx *ctx, void *handle);
+int hb_peer_connect(hb_ctx *ctx, int rank, int n_ranks, const void *handles);
+/* the same for contexts of one process (ctxs[rank] == ctx; several devices, or several contexts on one) */
+int hb_peer_connect_local(hb_ctx *ctx, int rank, int n_ranks, hb_ctx *const *ctxs);
+int hb_shard_exchange(hb_ctx *ctx, uint64_t seq, uint64_t *d_entry_base);
+int hb_peer_close(hb_ctx *ctx);
 /* Second half: fix every tile's entry offset / output base from
  * d_entry_base[0..1] (NULL = entry 0, base 0) and write the shard's symbols to
  * d_out[0 .. n).  Must follow hb_shard_map on the same context with the same

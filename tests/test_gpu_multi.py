@@ -98,3 +98,86 @@ def test_onethread_matches_oracle():
         assert res["n_symbols"] == f.usize
         assert O.sha256(out) == O.CORPORA[name][2]
         ctx.close()
+
+
+@pytest.mark.parametrize("name,nshards,order", [("kjv", 2, "up"), ("kjv", 8, "down"), ("paper1", 3, "down"),
+                                                ("ecoli", 4, "down"), ("bible", 5, "up")])
+def test_peer_exchange_replaces_allgather_and_compose(name, nshards, order):
+    """hb_shard_exchange: every rank stores its map into the exchange tables of the ranks to its right
+    (peer stores) and waits for the maps of the ranks to its left in ONE kernel.  Ranks = contexts of this
+    process with their own streams, spread over the devices of the box (one device works: the kernels of
+    different streams run side by side); "down" queues the LAST rank first, so that its kernel really has
+    to wait for flags that are not there yet.  Three decodes in a row: the ring slots move with seq."""
+    f = _stream(name)
+    want = O.simple_decode(O.Stream(f.tree, f.data, f.bits, f.usize))
+    ndev = torch.cuda.device_count()
+    per = (f.nbytes // nshards) // 16 * 16
+    bounds = [r * per for r in range(nshards)] + [f.nbytes]
+    ctxs = [hb.Context(r % ndev) for r in range(nshards)]
+    cbs = [hb.Codebook(c, f.tree) for c in ctxs]
+    hb.peer_connect_local(ctxs)
+    shards = []
+    for r in range(nshards):
+        dev = torch.device("cuda", r % ndev)
+        a, b = bounds[r], bounds[r + 1]
+        last = r == nshards - 1
+        bits_own = f.bits - 8 * a if last else 8 * (b - a)
+        halo_end = min(f.nbytes, b + 16)
+        bits_avail = bits_own if last else min(f.bits - 8 * a, 8 * (halo_end - a))
+        nb = halo_end - a
+        comp = torch.zeros((nb + 15) // 16 * 16 + 32, dtype=torch.uint8, device=dev)
+        comp[:nb] = torch.from_numpy(np.ascontiguousarray(f.data[a:halo_end])).to(dev)
+        eb = torch.zeros(4, dtype=torch.int64, device=dev)
+        out = torch.zeros(want.size + 64, dtype=torch.uint8, device=dev)
+        shards.append((comp, bits_own, bits_avail, eb, out))
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+    ranks = list(range(nshards)) if order == "up" else list(range(nshards - 1, -1, -1))
+    for seq in (1, 2, 3):
+        for r in ranks:
+            comp, bo, ba, eb, out = shards[r]
+            hb.shard_map(ctxs[r], cbs[r], comp.data_ptr(), comp.numel(), bo, ba, 0)
+            hb.shard_exchange(ctxs[r], seq, eb.data_ptr())
+        pieces, base_expect = [None] * nshards, 0
+        results = {}
+        for r in ranks:
+            comp, bo, ba, eb, out = shards[r]
+            results[r] = hb.shard_emit(ctxs[r], cbs[r], comp.data_ptr(), comp.numel(), bo, ba, eb.data_ptr(),
+                                       out.data_ptr(), want.size)
+        for r in range(nshards):
+            res = results[r]
+            assert res["out_base"] == base_expect, (seq, r)
+            base_expect += res["n_symbols"]
+            pieces[r] = shards[r][4][: res["n_symbols"]].cpu().numpy()
+            assert int(shards[r][3][2]) == base_expect          # symbols through this rank
+        got = np.concatenate(pieces)
+        assert got.size == want.size and np.array_equal(got, want), seq
+    for cb in cbs:
+        cb.close()
+    for c in ctxs:
+        c.close()
+
+
+def test_peer_exchange_times_out_instead_of_hanging():
+    """a rank whose left neighbour never delivers reports HB_ERR_STATE after the kernel's 5 s limit"""
+    f = _stream("paper1")
+    ctxs = [hb.Context(0), hb.Context(0)]
+    cbs = [hb.Codebook(c, f.tree) for c in ctxs]
+    hb.peer_connect_local(ctxs)
+    dev = torch.device("cuda", 0)
+    nb = f.nbytes
+    comp = torch.zeros((nb + 15) // 16 * 16 + 32, dtype=torch.uint8, device=dev)
+    comp[:nb] = torch.from_numpy(np.ascontiguousarray(f.data[:nb])).to(dev)
+    eb = torch.zeros(4, dtype=torch.int64, device=dev)
+    out = torch.zeros(f.usize + 64, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    hb.shard_map(ctxs[1], cbs[1], comp.data_ptr(), comp.numel(), f.bits, f.bits, 0)
+    hb.shard_exchange(ctxs[1], 7, eb.data_ptr())          # rank 0 never runs
+    with pytest.raises(hb.HuffError) as e:
+        hb.shard_emit(ctxs[1], cbs[1], comp.data_ptr(), comp.numel(), f.bits, f.bits, eb.data_ptr(),
+                      out.data_ptr(), f.usize)
+    assert e.value.code == -9
+    for cb in cbs:
+        cb.close()
+    for c in ctxs:
+        c.close()
