@@ -549,6 +549,9 @@ def main():
             "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
+    if PEER["on"]:          # unmap the neighbours' exchange tables everywhere before any of them is freed
+        hb.peer_disconnect(ctx)
+        dist.barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -156,6 +156,7 @@ def lib():
     L.hb_peer_connect_local.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.hb_shard_exchange.argtypes = [vp, u64, vp]
     L.hb_peer_close.argtypes = [vp]
+    L.hb_peer_disconnect.argtypes = [vp]
     L.hb_shard_emit.argtypes = [vp, vp, vp, u64, u64, u64, vp, vp, u64, C.POINTER(Result)]
     L.hb_decode_host.argtypes = [vp, vp, i32, vp, u64, vp, u64, C.POINTER(Result)]
     L.hb_huff_load.argtypes = [C.c_char_p, C.POINTER(HuffFileC)]
@@ -473,6 +474,11 @@ def peer_connect_local(ctxs) -> None:
     arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
     for r, c in enumerate(ctxs):
         _check(lib().hb_peer_connect_local(c.h, r, len(ctxs), arr), "hb_peer_connect_local", c.h)
+
+
+def peer_disconnect(ctx) -> None:
+    """hb_peer_disconnect: unmap the other ranks' tables (call on every rank, then a barrier, before closing)."""
+    _check(lib().hb_peer_disconnect(ctx.h), "hb_peer_disconnect", ctx.h)
 
 
 def shard_exchange(ctx, seq: int, d_entry_base: int) -> None:

@@ -1145,18 +1145,26 @@ hb_exchange_kernel(const uint64_t *__restrict__ my_map, hb_peer_tabs tabs, const
     }
 }
 
-extern "C" int hb_peer_close(hb_ctx *ctx) {
+/* unmap the other ranks' tables (this rank's own table stays: others may still store into it) */
+extern "C" int hb_peer_disconnect(hb_ctx *ctx) {
     if (!ctx) return HB_ERR_ARG;
     cudaSetDevice(ctx->device);
-    if (ctx->peer_tab || ctx->peer_n) cudaStreamSynchronize(ctx->stream);
+    if (ctx->peer_n) cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < HB_MULTI_MAX; r++)
         if (ctx->peer_ptr[r]) {
             if (ctx->peer_ipc) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
             ctx->peer_ptr[r] = nullptr;
         }
-    if (ctx->peer_tab) { cudaFree(ctx->peer_tab); ctx->peer_tab = nullptr; }
     ctx->peer_rank = -1;
     ctx->peer_n = 0;
+    cudaGetLastError();
+    return HB_OK;
+}
+
+extern "C" int hb_peer_close(hb_ctx *ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    hb_peer_disconnect(ctx);
+    if (ctx->peer_tab) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->peer_tab); ctx->peer_tab = nullptr; }
     cudaGetLastError();
     return HB_OK;
 }

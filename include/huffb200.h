@@ -217,6 +217,10 @@ int hb_peer_connect(hb_ctx *ctx, int rank, int n_ranks, const void *handles);
 /* the same for contexts of one process (ctxs[rank] == ctx; several devices, or several contexts on one) */
 int hb_peer_connect_local(hb_ctx *ctx, int rank, int n_ranks, hb_ctx *const *ctxs);
 int hb_shard_exchange(hb_ctx *ctx, uint64_t seq, uint64_t *d_entry_base);
+/* Teardown: hb_peer_disconnect unmaps the other ranks' tables; hb_peer_close also frees this rank's own
+ * (hb_ctx_destroy calls it).  With several processes: disconnect everywhere, a barrier, then close, so
+ * that no table is freed while a neighbour still has it mapped. */
+int hb_peer_disconnect(hb_ctx *ctx);
 int hb_peer_close(hb_ctx *ctx);
 /* Second half: fix every tile's entry offset / output base from
  * d_entry_base[0..1] (NULL = entry 0, base 0) and write the shard's symbols to
