@@ -77,6 +77,7 @@ __global__ void hb_push_map_kernel(const uint64_t *__restrict__ src, hb_peer_map
 struct hb_multi {
     int n = 0;
     bool push_ok = false;          /* every device can store into every other device's memory */
+    bool xchg_ok = false;          /* ... and the contexts are connected for hb_shard_exchange (the default) */
     hb_pool *pool = nullptr;
     std::atomic<uint64_t> map_issued[HB_MULTI_MAX];   /* run number whose ev_map record has been queued */
     std::atomic<int> abort_run{0};
@@ -240,7 +241,17 @@ extern "C" int hb_multi_create(const int *devices, int n_devices, hb_multi **out
         }
     }
     cudaGetLastError();
-    m->push_ok = all_peers && !(getenv("HB_MULTI_PUSH") && getenv("HB_MULTI_PUSH")[0] == '0');
+    /* HB_MULTI_PUSH: 0 = peer copies pulled by the receiver, 1 = hb_push_map_kernel + events + hb_shard_compose,
+     * unset / 2 = hb_shard_exchange (stores, wait and composition in one kernel, no host-side ordering) */
+    const char *pm = getenv("HB_MULTI_PUSH");
+    m->push_ok = all_peers && !(pm && pm[0] == '0');
+    if (m->push_ok && !(pm && pm[0] == '1')) {
+        hb_ctx *cs[HB_MULTI_MAX];
+        for (int i = 0; i < m->n; i++) cs[i] = m->d[i].ctx;
+        bool ok = true;
+        for (int i = 0; i < m->n && ok; i++) ok = hb_peer_connect_local(cs[i], i, m->n, cs) == HB_OK;
+        m->xchg_ok = ok;
+    }
     for (int i = 0; i < HB_MULTI_MAX; i++) m->map_issued[i].store(0);
     if (m->n > 1 && !(getenv("HB_MULTI_THREADS") && getenv("HB_MULTI_THREADS")[0] == '0')) {
         m->pool = new (std::nothrow) hb_pool();
@@ -342,6 +353,13 @@ static int dev_map(hb_multi *m, int i, uint64_t run, bool upload, const uint8_t 
     rc = e == cudaSuccess ? hb_ctx_set_shard_origin(v.ctx, v.a, 1) : HB_ERR_CUDA;
     if (rc == HB_OK)
         rc = hb_shard_map(v.ctx, v.cb, v.d_comp, v.readable, v.bits_own, v.bits_avail, v.d_maps + 32 * i);
+    if (rc == HB_OK && m->xchg_ok) {
+        /* stores into the right neighbours' tables, wait for the left neighbours, composition: one kernel */
+        rc = hb_shard_exchange(v.ctx, run, v.d_eb);
+        m->map_issued[i].store(run, std::memory_order_release);
+        if (rc != HB_OK) return dev_fail(m, i, rc, "hb_shard_exchange");
+        return HB_OK;
+    }
     if (rc == HB_OK && m->push_ok && i + 1 < m->n_active) {
         hb_peer_maps pm;
         int np = 0;
