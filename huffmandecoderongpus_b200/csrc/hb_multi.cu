@@ -3,12 +3,15 @@
  *
  * The reference has no multi-GPU path; SURVEY.md 8(b)(3)/8(e) ask for one under the approach
  * table.  A stream is cut into N contiguous byte ranges (16-byte aligned, 16-byte halo); every
- * device computes its shard's 32-entry transfer map (hb_shard_map) and stores it straight into
- * the map tables of the devices to its right over NVLink (hb_push_map_kernel: peer stores, one
- * launch; where a pair of devices has no peer access the right-hand device pulls the 256 bytes
- * with cudaMemcpyPeerAsync instead), ordered by events: no NCCL, no host round trip.  Every
- * device composes the maps to its left (hb_shard_compose) and emits its shard into its own
- * output slice (hb_shard_emit).  Nothing here decodes on the CPU.
+ * device computes its shard's 32-entry transfer map (hb_shard_map), stores it straight into the
+ * exchange tables of the devices to its right over NVLink, waits for the maps of the devices to
+ * its left and composes them -- hb_shard_exchange, ONE kernel, the contexts connected with
+ * hb_peer_connect_local: no NCCL, no copy engine, no host round trip, no ordering between the
+ * device threads -- and emits its shard into its own output slice (hb_shard_emit).  Two earlier
+ * forms of the exchange are kept behind HB_MULTI_PUSH: 1 = hb_push_map_kernel (peer stores) +
+ * events + hb_shard_compose, 0 = the right-hand device pulls the 256 bytes with
+ * cudaMemcpyPeerAsync (what is used where a pair of devices has no peer access).  Nothing here
+ * decodes on the CPU.
  *
  * Two ways in:
  *   resident   hb_multi_load / hb_multi_generate, then hb_multi_decode (device-timed: CUDA

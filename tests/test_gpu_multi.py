@@ -1,5 +1,5 @@
 """One process, N devices (hb_multi_*, b200ApproachMulti): byte-range shards, maps exchanged
-by peer copies.  Runs with however many GPUs the box has (1 works: a single shard); on a
+by peer stores (hb_shard_exchange), and the exchange kernel itself over contexts of this process.  Runs with however many GPUs the box has (1 works: a single shard); on a
 multi-GPU box the 2-, 4- and 8-device splits are exercised as well."""
 import numpy as np
 import pytest
