@@ -241,9 +241,10 @@ class Job:
         self.all_maps = torch.zeros(32 * world, dtype=torch.int64, device=dev)
         self.eb = torch.zeros(4, dtype=torch.int64, device=dev)
         # ---- correctness of this very configuration (untimed) ----
+        self.barrier()             # ranks aligned: hb_shard_exchange gives a left neighbour 5 s to deliver its map
         res = self.step(want_result=True)
         self.n_mine, self.out_base = res["n_symbols"], res["out_base"]
-        self.launches_per_step = res["launches"] + (1 if world > 1 else 0)   # + hb_compose_kernel
+        self.launches_per_step = res["launches"] + (1 if world > 1 else 0)   # + hb_exchange_kernel / hb_compose_kernel
         self.verify_device(self.out, "device-resident decode")
 
     def verify_device(self, out_tensor, what):
